@@ -1,0 +1,57 @@
+// sse_device.cuh -- device-side data layout shared by the kernels and the host library.
+//
+// HBM layout (one context per GPU):
+//   in      u8[in_arena_bytes]         micro-batch input: per-connection segments, 16-byte aligned
+//   segs    sse_seg[max_segs]          segment descriptors (conn, in_off, in_len, mode)
+//   conns   ConnState[max_conns]       persistent per-connection state (carry length, flags)
+//   carry   u8[max_conns*carry_slot]   persistent held-back tail of each connection (provider.go:322
+//                                      ReadBytes would keep these bytes inside bufio.Reader)
+//   out, frames, recs, tcs, usages, text, runs, seg_results   per-batch results (see include/sse_gpu.h)
+//   ctr     Counters                   bump allocators + work ticket, zeroed per launch
+#pragma once
+#include <stdint.h>
+#include "../../include/sse_gpu.h"
+
+struct ConnState {
+    uint32_t carry_len;
+    uint32_t flags;
+};
+#define CONN_FINISHED 1u   // mode R: terminating chunk seen (agent.go:235-242); later bytes are never read
+#define CONN_DEAD     2u   // line exceeded carry_slot_bytes
+#define CONN_LONG     4u   // a line longer than the smem window is being assembled in the carry slot
+
+struct Counters {
+    uint32_t ticket;       // next segment to process
+    uint32_t out_bytes;
+    uint32_t n_frames;
+    uint32_t n_recs;
+    uint32_t n_tcs;
+    uint32_t n_usages;
+    uint32_t text_bytes;
+    uint32_t n_runs;
+    int32_t  status;
+    uint32_t pad[7];
+};
+
+struct KParams {
+    const uint8_t *in;
+    const sse_seg *segs;
+    uint32_t n_segs;
+    uint32_t max_conns;
+    ConnState *conns;
+    uint8_t *carry;
+    uint32_t carry_slot;
+    // results
+    uint8_t *out;            uint32_t cap_out;
+    sse_frame *frames;       uint32_t cap_frames;
+    sse_rec *recs;           uint32_t cap_recs;
+    sse_tc *tcs;             uint32_t cap_tcs;
+    sse_usage *usages;       uint32_t cap_usages;
+    uint8_t *text;           uint32_t cap_text;
+    sse_run *runs;           uint32_t cap_runs;
+    sse_seg_result *seg_results;
+    Counters *ctr;
+};
+
+// launch wrappers (sse_kernel.cu)
+int sse_launch_stream_kernel(const KParams &p, void *stream, int sm_count);

@@ -1,0 +1,343 @@
+// sse_host.cu -- C ABI of libssegpu.so (include/sse_gpu.h): context, pinned staging, batch pipeline.
+//
+// One context per GPU. A batch slot owns pinned host staging + device buffers + a CUDA stream:
+//   sse_submit:  H2D(segs, input)  ->  [wait: previous batch's kernel]  ->  kernel  ->  D2H(counters)
+//   sse_collect: sync, then exact-size D2H of the result arrays, sync.
+// Kernels of consecutive batches are ordered by an event because they share per-connection state
+// (carry, finished flag) -- the per-connection FIFO of provider.go:307-340; H2D of batch k+1 and D2H of
+// batch k overlap kernel k on their own streams.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <vector>
+#include "sse_device.cuh"
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+bool cu_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+    return false;
+}
+#define CU(call) do { if (!cu_ok((call), #call)) return SSE_ERR_CUDA; } while (0)
+
+enum SlotState { SLOT_FREE = 0, SLOT_ACQUIRED, SLOT_SUBMITTED, SLOT_COLLECTED };
+
+struct Slot {
+    int state = SLOT_FREE;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t kernel_done = nullptr;
+    // host (pinned)
+    uint8_t *h_in = nullptr; sse_seg *h_segs = nullptr;
+    uint8_t *h_out = nullptr; sse_frame *h_frames = nullptr; sse_rec *h_recs = nullptr; sse_tc *h_tcs = nullptr;
+    sse_usage *h_usages = nullptr; uint8_t *h_text = nullptr; sse_run *h_runs = nullptr; sse_seg_result *h_segres = nullptr;
+    Counters *h_ctr = nullptr;
+    // device
+    uint8_t *d_in = nullptr; sse_seg *d_segs = nullptr;
+    uint8_t *d_out = nullptr; sse_frame *d_frames = nullptr; sse_rec *d_recs = nullptr; sse_tc *d_tcs = nullptr;
+    sse_usage *d_usages = nullptr; uint8_t *d_text = nullptr; sse_run *d_runs = nullptr; sse_seg_result *d_segres = nullptr;
+    Counters *d_ctr = nullptr;
+    uint32_t n_segs = 0, in_bytes = 0;
+};
+
+} // namespace
+
+struct sse_ctx {
+    int device = 0;
+    int sm_count = 0;
+    sse_config cfg{};
+    ConnState *d_conns = nullptr;
+    uint8_t *d_carry = nullptr;
+    cudaStream_t ctl_stream = nullptr;
+    cudaEvent_t last_kernel = nullptr;   // completion of the most recently launched kernel
+    bool have_last = false;
+    std::vector<Slot> slots;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+template <class T> bool dalloc(T *&p, size_t n) { return cu_ok(cudaMalloc((void **)&p, n ? n * sizeof(T) : sizeof(T)), "cudaMalloc"); }
+template <class T> bool halloc(T *&p, size_t n) { return cu_ok(cudaHostAlloc((void **)&p, n ? n * sizeof(T) : sizeof(T), cudaHostAllocDefault), "cudaHostAlloc"); }
+
+void free_slot(Slot &s) {
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.kernel_done) cudaEventDestroy(s.kernel_done);
+    cudaFreeHost(s.h_in); cudaFreeHost(s.h_segs); cudaFreeHost(s.h_out); cudaFreeHost(s.h_frames); cudaFreeHost(s.h_recs);
+    cudaFreeHost(s.h_tcs); cudaFreeHost(s.h_usages); cudaFreeHost(s.h_text); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_segres);
+    cudaFreeHost(s.h_ctr);
+    cudaFree(s.d_in); cudaFree(s.d_segs); cudaFree(s.d_out); cudaFree(s.d_frames); cudaFree(s.d_recs); cudaFree(s.d_tcs);
+    cudaFree(s.d_usages); cudaFree(s.d_text); cudaFree(s.d_runs); cudaFree(s.d_segres); cudaFree(s.d_ctr);
+}
+
+KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
+    KParams p{};
+    p.in = s.d_in; p.segs = s.d_segs; p.n_segs = n_segs; p.max_conns = c->cfg.max_conns;
+    p.conns = c->d_conns; p.carry = c->d_carry; p.carry_slot = c->cfg.carry_slot_bytes;
+    p.out = s.d_out; p.cap_out = c->cfg.out_arena_bytes;
+    p.frames = s.d_frames; p.cap_frames = c->cfg.max_frames;
+    p.recs = s.d_recs; p.cap_recs = c->cfg.max_recs;
+    p.tcs = s.d_tcs; p.cap_tcs = c->cfg.max_tcs;
+    p.usages = s.d_usages; p.cap_usages = c->cfg.max_usages;
+    p.text = s.d_text; p.cap_text = c->cfg.text_arena_bytes;
+    p.runs = s.d_runs; p.cap_runs = c->cfg.max_runs;
+    p.seg_results = s.d_segres; p.ctr = s.d_ctr;
+    return p;
+}
+
+int validate_segs(sse_ctx *c, Slot &s, uint32_t n_segs, uint32_t in_bytes) {
+    if (n_segs > c->cfg.max_segs || in_bytes > c->cfg.in_arena_bytes) return SSE_ERR_ARG;
+    for (uint32_t i = 0; i < n_segs; i++) {
+        const sse_seg &g = s.h_segs[i];
+        if (g.conn >= c->cfg.max_conns || (g.in_off & 15u) || (uint64_t)g.in_off + g.in_len > in_bytes) return SSE_ERR_ARG;
+    }
+    return SSE_OK;
+}
+
+int do_upload(sse_ctx *c, Slot &s, uint32_t n_segs, uint32_t in_bytes, cudaStream_t st) {
+    if (n_segs) CU(cudaMemcpyAsync(s.d_segs, s.h_segs, (size_t)n_segs * sizeof(sse_seg), cudaMemcpyHostToDevice, st));
+    if (in_bytes) CU(cudaMemcpyAsync(s.d_in, s.h_in, ((size_t)in_bytes + 15) & ~(size_t)15, cudaMemcpyHostToDevice, st));
+    s.n_segs = n_segs; s.in_bytes = in_bytes;
+    (void)c;
+    return SSE_OK;
+}
+
+int do_launch(sse_ctx *c, Slot &s, uint32_t n_segs, cudaStream_t st) {
+    CU(cudaMemsetAsync(s.d_ctr, 0, sizeof(Counters), st));
+    if (n_segs) {
+        KParams p = make_params(c, s, n_segs);
+        int e = sse_launch_stream_kernel(p, (void *)st, c->sm_count);
+        if (e != 0) { cu_ok((cudaError_t)e, "sse_stream_kernel launch"); return SSE_ERR_CUDA; }
+        c->launches++;
+    }
+    s.n_segs = n_segs;
+    return SSE_OK;
+}
+
+int do_download(sse_ctx *c, Slot &s, sse_result *res, cudaStream_t st) {
+    CU(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const Counters k = *s.h_ctr;
+    memset(res, 0, sizeof *res);
+    res->status = k.status;
+    res->n_segs = s.n_segs;
+    if (k.status != SSE_OK) {   // overflow: the batch result is unusable, report loudly
+        return k.status;
+    }
+    res->n_frames = k.n_frames; res->n_recs = k.n_recs; res->n_tcs = k.n_tcs; res->n_usages = k.n_usages;
+    res->n_runs = k.n_runs; res->out_bytes = k.out_bytes; res->text_bytes = k.text_bytes;
+    if (k.out_bytes) CU(cudaMemcpyAsync(s.h_out, s.d_out, k.out_bytes, cudaMemcpyDeviceToHost, st));
+    if (k.n_frames) CU(cudaMemcpyAsync(s.h_frames, s.d_frames, (size_t)k.n_frames * sizeof(sse_frame), cudaMemcpyDeviceToHost, st));
+    if (k.n_recs) CU(cudaMemcpyAsync(s.h_recs, s.d_recs, (size_t)k.n_recs * sizeof(sse_rec), cudaMemcpyDeviceToHost, st));
+    if (k.n_tcs) CU(cudaMemcpyAsync(s.h_tcs, s.d_tcs, (size_t)k.n_tcs * sizeof(sse_tc), cudaMemcpyDeviceToHost, st));
+    if (k.n_usages) CU(cudaMemcpyAsync(s.h_usages, s.d_usages, (size_t)k.n_usages * sizeof(sse_usage), cudaMemcpyDeviceToHost, st));
+    if (k.text_bytes) CU(cudaMemcpyAsync(s.h_text, s.d_text, k.text_bytes, cudaMemcpyDeviceToHost, st));
+    if (k.n_runs) CU(cudaMemcpyAsync(s.h_runs, s.d_runs, (size_t)k.n_runs * sizeof(sse_run), cudaMemcpyDeviceToHost, st));
+    if (s.n_segs) CU(cudaMemcpyAsync(s.h_segres, s.d_segres, (size_t)s.n_segs * sizeof(sse_seg_result), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    res->out = s.h_out; res->frames = s.h_frames; res->recs = s.h_recs; res->tcs = s.h_tcs; res->usages = s.h_usages;
+    res->text = s.h_text; res->runs = s.h_runs; res->segs = s.h_segres;
+    (void)c;
+    return SSE_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sse_abi_version(void) { return SSE_ABI_VERSION; }
+
+const char *sse_last_cuda_error(void) { return g_cuda_err; }
+
+const char *sse_strerror(int status) {
+    switch (status) {
+    case SSE_OK: return "ok";
+    case SSE_ERR_NO_DEVICE: return "no CUDA device available (libssegpu has no CPU fallback)";
+    case SSE_ERR_CUDA: return "CUDA error (see sse_last_cuda_error)";
+    case SSE_ERR_ARG: return "invalid argument";
+    case SSE_ERR_BUSY: return "batch slot busy or in the wrong state";
+    case SSE_ERR_OVERFLOW: return "result arena overflow: batch discarded (increase sse_config capacities)";
+    case SSE_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+    }
+}
+
+void sse_default_config(sse_config *cfg, uint32_t max_conns, uint32_t bytes_per_batch) {
+    memset(cfg, 0, sizeof *cfg);
+    cfg->struct_size = sizeof *cfg;
+    cfg->max_conns = max_conns;
+    cfg->max_segs = max_conns;
+    uint64_t in = ((uint64_t)bytes_per_batch + 16ull * max_conns + 4095) & ~4095ull;
+    cfg->in_arena_bytes = (uint32_t)(in > 0xF0000000ull ? 0xF0000000ull : in);
+    uint64_t out = in + in / 8 + 65536;
+    cfg->out_arena_bytes = (uint32_t)(out > 0xF0000000ull ? 0xF0000000ull : out);
+    cfg->max_frames = (uint32_t)(in / 32 + 4ull * max_conns + 1024);
+    cfg->max_recs = (uint32_t)(in / 64 + 2ull * max_conns + 1024);
+    cfg->max_tcs = (uint32_t)(in / 256 + 1024);
+    cfg->max_usages = cfg->max_recs;
+    cfg->text_arena_bytes = (uint32_t)(in / 4 + 65536);
+    cfg->max_runs = max_conns + 1024;
+    cfg->carry_slot_bytes = 16384;
+    cfg->n_slots = 2;
+}
+
+int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
+    if (!cfg || !out || cfg->struct_size != sizeof(sse_config)) return SSE_ERR_ARG;
+    if (cfg->n_slots < 1 || cfg->n_slots > 8 || cfg->max_conns == 0 || cfg->max_segs == 0 ||
+        (cfg->in_arena_bytes & 15u) || cfg->carry_slot_bytes < 8192 + 16) return SSE_ERR_ARG;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) {
+        cu_ok(cudaGetLastError(), "cudaGetDeviceCount");
+        return SSE_ERR_NO_DEVICE;
+    }
+    CU(cudaSetDevice(device));
+    sse_ctx *c = new (std::nothrow) sse_ctx();
+    if (!c) return SSE_ERR_NOMEM;
+    c->device = device; c->cfg = *cfg;
+    cudaDeviceProp prop;
+    if (!cu_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete c; return SSE_ERR_CUDA; }
+    c->sm_count = prop.multiProcessorCount;
+    bool ok = true;
+    ok = ok && cu_ok(cudaStreamCreateWithFlags(&c->ctl_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    ok = ok && cu_ok(cudaEventCreateWithFlags(&c->last_kernel, cudaEventDisableTiming), "cudaEventCreate");
+    ok = ok && dalloc(c->d_conns, cfg->max_conns);
+    ok = ok && dalloc(c->d_carry, (size_t)cfg->max_conns * cfg->carry_slot_bytes);
+    ok = ok && cu_ok(cudaMemset(c->d_conns, 0, (size_t)cfg->max_conns * sizeof(ConnState)), "cudaMemset");
+    c->slots.resize(cfg->n_slots);
+    for (auto &s : c->slots) {
+        if (!ok) break;
+        ok = ok && cu_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        ok = ok && cu_ok(cudaEventCreateWithFlags(&s.kernel_done, cudaEventDisableTiming), "cudaEventCreate");
+        ok = ok && halloc(s.h_in, (size_t)cfg->in_arena_bytes + 16) && halloc(s.h_segs, cfg->max_segs);
+        ok = ok && halloc(s.h_out, cfg->out_arena_bytes) && halloc(s.h_frames, cfg->max_frames) && halloc(s.h_recs, cfg->max_recs);
+        ok = ok && halloc(s.h_tcs, cfg->max_tcs) && halloc(s.h_usages, cfg->max_usages) && halloc(s.h_text, cfg->text_arena_bytes);
+        ok = ok && halloc(s.h_runs, cfg->max_runs) && halloc(s.h_segres, cfg->max_segs) && halloc(s.h_ctr, 1);
+        ok = ok && dalloc(s.d_in, (size_t)cfg->in_arena_bytes + 16) && dalloc(s.d_segs, cfg->max_segs);
+        ok = ok && dalloc(s.d_out, cfg->out_arena_bytes) && dalloc(s.d_frames, cfg->max_frames) && dalloc(s.d_recs, cfg->max_recs);
+        ok = ok && dalloc(s.d_tcs, cfg->max_tcs) && dalloc(s.d_usages, cfg->max_usages) && dalloc(s.d_text, cfg->text_arena_bytes);
+        ok = ok && dalloc(s.d_runs, cfg->max_runs) && dalloc(s.d_segres, cfg->max_segs) && dalloc(s.d_ctr, 1);
+    }
+    if (!ok) { sse_destroy(c); return SSE_ERR_CUDA; }
+    *out = c;
+    return SSE_OK;
+}
+
+void sse_destroy(sse_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &s : c->slots) free_slot(s);
+    cudaFree(c->d_conns); cudaFree(c->d_carry);
+    if (c->ctl_stream) cudaStreamDestroy(c->ctl_stream);
+    if (c->last_kernel) cudaEventDestroy(c->last_kernel);
+    delete c;
+}
+
+int sse_acquire(sse_ctx *c, int *slot, sse_batch *batch) {
+    if (!c || !slot || !batch) return SSE_ERR_ARG;
+    for (size_t i = 0; i < c->slots.size(); i++) {
+        if (c->slots[i].state == SLOT_FREE) {
+            Slot &s = c->slots[i];
+            s.state = SLOT_ACQUIRED;
+            *slot = (int)i;
+            batch->in_arena = s.h_in; batch->segs = s.h_segs;
+            batch->in_arena_bytes = c->cfg.in_arena_bytes; batch->max_segs = c->cfg.max_segs;
+            return SSE_OK;
+        }
+    }
+    return SSE_ERR_BUSY;
+}
+
+int sse_submit(sse_ctx *c, int slot, uint32_t n_segs, uint32_t in_bytes) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return SSE_ERR_ARG;
+    Slot &s = c->slots[slot];
+    if (s.state != SLOT_ACQUIRED) return SSE_ERR_BUSY;
+    int rc = validate_segs(c, s, n_segs, in_bytes);
+    if (rc != SSE_OK) return rc;
+    CU(cudaSetDevice(c->device));
+    rc = do_upload(c, s, n_segs, in_bytes, s.stream);
+    if (rc != SSE_OK) return rc;
+    if (c->have_last) CU(cudaStreamWaitEvent(s.stream, c->last_kernel, 0));   // per-connection FIFO across batches
+    rc = do_launch(c, s, n_segs, s.stream);
+    if (rc != SSE_OK) return rc;
+    CU(cudaEventRecord(c->last_kernel, s.stream));
+    c->have_last = true;
+    s.state = SLOT_SUBMITTED;
+    return SSE_OK;
+}
+
+int sse_collect(sse_ctx *c, int slot, sse_result *res) {
+    if (!c || !res || slot < 0 || slot >= (int)c->slots.size()) return SSE_ERR_ARG;
+    Slot &s = c->slots[slot];
+    if (s.state != SLOT_SUBMITTED) return SSE_ERR_BUSY;
+    CU(cudaSetDevice(c->device));
+    int rc = do_download(c, s, res, s.stream);
+    s.state = SLOT_COLLECTED;
+    return rc;
+}
+
+int sse_release(sse_ctx *c, int slot) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return SSE_ERR_ARG;
+    Slot &s = c->slots[slot];
+    if (s.state == SLOT_SUBMITTED) { CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(s.stream)); }
+    s.state = SLOT_FREE;
+    return SSE_OK;
+}
+
+int sse_reset_conn(sse_ctx *c, uint32_t conn) {
+    if (!c || conn >= c->cfg.max_conns) return SSE_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    if (c->have_last) CU(cudaStreamWaitEvent(c->ctl_stream, c->last_kernel, 0));
+    CU(cudaMemsetAsync(c->d_conns + conn, 0, sizeof(ConnState), c->ctl_stream));
+    CU(cudaEventRecord(c->last_kernel, c->ctl_stream));   // later kernels are ordered after the reset
+    c->have_last = true;
+    return SSE_OK;
+}
+
+int sse_reset_all(sse_ctx *c, void *cuda_stream) {
+    if (!c) return SSE_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->ctl_stream;
+    if (!cuda_stream && c->have_last) CU(cudaStreamWaitEvent(st, c->last_kernel, 0));
+    CU(cudaMemsetAsync(c->d_conns, 0, (size_t)c->cfg.max_conns * sizeof(ConnState), st));
+    if (!cuda_stream) { CU(cudaEventRecord(c->last_kernel, st)); c->have_last = true; }
+    return SSE_OK;
+}
+
+int sse_upload(sse_ctx *c, int slot, uint32_t n_segs, uint32_t in_bytes, void *cuda_stream) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return SSE_ERR_ARG;
+    Slot &s = c->slots[slot];
+    if (s.state != SLOT_ACQUIRED) return SSE_ERR_BUSY;
+    int rc = validate_segs(c, s, n_segs, in_bytes);
+    if (rc != SSE_OK) return rc;
+    CU(cudaSetDevice(c->device));
+    return do_upload(c, s, n_segs, in_bytes, cuda_stream ? (cudaStream_t)cuda_stream : s.stream);
+}
+
+int sse_launch(sse_ctx *c, int slot, uint32_t n_segs, void *cuda_stream) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return SSE_ERR_ARG;
+    Slot &s = c->slots[slot];
+    if (s.state != SLOT_ACQUIRED || n_segs > c->cfg.max_segs) return SSE_ERR_BUSY;
+    CU(cudaSetDevice(c->device));
+    return do_launch(c, s, n_segs, cuda_stream ? (cudaStream_t)cuda_stream : s.stream);
+}
+
+int sse_download(sse_ctx *c, int slot, sse_result *res, void *cuda_stream) {
+    if (!c || !res || slot < 0 || slot >= (int)c->slots.size()) return SSE_ERR_ARG;
+    Slot &s = c->slots[slot];
+    if (s.state != SLOT_ACQUIRED) return SSE_ERR_BUSY;
+    CU(cudaSetDevice(c->device));
+    return do_download(c, s, res, cuda_stream ? (cudaStream_t)cuda_stream : s.stream);
+}
+
+int sse_launch_count(sse_ctx *c, uint64_t *kernel_launches) {
+    if (!c || !kernel_launches) return SSE_ERR_ARG;
+    *kernel_launches = c->launches;
+    return SSE_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """One GPU context for the whole session (the product path: libssegpu.so through its C ABI)."""
+    from inference_gateway_b200 import SseEngine
+    eng = SseEngine(device=0, max_conns=4096, bytes_per_batch=8 << 20, carry_slot_bytes=65536, n_slots=2)
+    yield eng
+    eng.close()

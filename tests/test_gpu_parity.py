@@ -1,0 +1,310 @@
+"""GPU parity: libssegpu.so (through its C ABI) vs the CPU oracle, bit-exact, on the same inputs.
+
+Covers SURVEY.md Appendix B vectors, the reference's own fixtures (tests/golden/ref_fixtures.json), the
+BASELINE.json configs at reduced stream counts, ragged/edge inputs and a JSON mutation fuzz.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from inference_gateway_b200 import _abi as A
+from inference_gateway_b200 import synth
+from oracle import orc
+from tests.util import agent_results, check_stream, run_streams, telemetry_results
+
+pytestmark = pytest.mark.gpu
+
+P, R, PP = A.MODE_P, A.MODE_R | A.MODE_PARSE, A.MODE_P | A.MODE_PARSE
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_fixtures.json")))["fixtures"]
+
+
+def _run_and_check(engine, bodies, modes, n_batches=1, seed=0, folds=False):
+    outs = run_streams(engine, bodies, modes, n_batches=n_batches, seed=seed, with_folds=folds)
+    views = [check_stream(b, m, o, label=f"stream {i} mode {m} batches {n_batches}")
+             for i, (b, m, o) in enumerate(zip(bodies, modes, outs))]
+    return outs, views
+
+
+# ------------------------------------------------------------------ SURVEY.md Appendix B
+APPENDIX_P = [
+    (b'data: {"a":1}\n\ndata: [DONE]\n\n', b'data: {"a":1}\n\ndata: [DONE]\n\n'),      # P1
+    (b"data: x\r\n\r\ndata: y", b"data: x\r\n\r\n"),                                  # P2: tail dropped
+    (b"", b""),                                                                       # P3
+    (b": ping\n\nevent: x\ndata: 1\n\n", b": ping\n\nevent: x\ndata: 1\n\n"),          # P4
+    (b"x" * 10000 + b"\n", b"x" * 10000 + b"\n"),                                     # P5: > bufio's 4096
+]
+
+
+def test_appendix_b_passthrough(engine):
+    bodies = [i for i, _ in APPENDIX_P]
+    outs, _ = _run_and_check(engine, bodies, [P] * len(bodies))
+    for (inp, exp), o in zip(APPENDIX_P, outs):
+        assert b"".join(o.frames) == exp
+    # P1 is delivered as 4 channel elements (provider.go:322-334)
+    assert outs[0].frames == [b'data: {"a":1}\n', b"\n", b"data: [DONE]\n", b"\n"]
+
+
+APPENDIX_R = [
+    (b'data: {"choices":[{"index":0,"delta":{"content":"Hi"},"finish_reason":null}]}\n',
+     [b'data: {"choices":[{"index":0,"delta":{"content":"Hi"},"finish_reason":null}]}\n\n']),     # R1
+    (b'\n: ping\nevent: m\ndata:{"x":1}\ndata: \n', []),                                           # R2
+    (b'  data: {"x":1} \r\n', [b'data: {"x":1}\n\n']),                                             # R3
+    (b'data:  {"x":1}\n', [b'data:  {"x":1}\n\n']),                                                # R4
+    (b"data: [DONE]\n", []),                                                                       # R5
+    (b'data: {"choices":[{"index":0,"delta":{"content":"say [DONE]"},"finish_reason":null}]}\n', []),  # R6
+    (b"data: {oops\n", [b"data: {oops\n\n"]),                                                      # R7
+    (b'data: {"choices":[{"index":0,"delta":{},"finish_reason":"stop"}]}\n\ndata: {"choices":[],"usage":{"prompt_tokens":1,"completion_tokens":2,"total_tokens":3}}\n\ndata: [DONE]\n\n',
+     [b'data: {"choices":[{"index":0,"delta":{},"finish_reason":"stop"}]}\n\n']),                   # R8
+]
+
+
+def test_appendix_b_reframe(engine):
+    bodies = [i for i, _ in APPENDIX_R]
+    outs, _ = _run_and_check(engine, bodies, [R] * len(bodies))
+    for (inp, exp), o in zip(APPENDIX_R, outs):
+        assert o.frames == exp, inp
+    assert outs[7].terminated
+
+
+# ------------------------------------------------------------------ reference fixtures
+def _fixture_bodies(fx):
+    for it in fx["iterations"]:
+        if fx["kind"] == "channel_elements":
+            yield ("\n".join(it) + "\n").encode()
+        else:
+            body = it[0]
+            yield (body if body.endswith("\n") else body + "\n").encode()
+
+
+@pytest.mark.parametrize("fx", [f for f in GOLD if "content" in f["expect"]], ids=lambda f: f["name"])
+def test_reference_fixtures_agent(engine, fx):
+    """The semantic assertions the reference tests make on these streams (cited in the golden file)."""
+    bodies = list(_fixture_bodies(fx))
+    outs, views = _run_and_check(engine, bodies, [R] * len(bodies), n_batches=3, seed=7, folds=True)
+    exp = fx["expect"]
+    fin_names = {1: "stop", 2: "tool_calls"}
+    for i, o in enumerate(outs):
+        content, has, term, fin, calls = agent_results(engine.L, o.agent)
+        assert content.decode() == exp["content"][i]
+        assert term and fin_names[fin] == exp["finish"][i]
+        want = exp["tool_calls"][i]
+        assert has == bool(want)
+        got = [dict(id=c["id"].decode(), name=c["name"].decode(), args=c["args"].decode()) for c in calls]
+        assert got == want
+        # frames never contain [DONE]; the agent appends exactly one at the very end (agent.go:140-143)
+        assert all(b"[DONE]" not in f for f in o.frames)
+        # same answers from the oracle's own restatement of agent.go:377-481
+        ocalls = orc.parse_tool_calls(views[i].builder)
+        assert [dict(id=c["id"].decode(), name=c["name"].decode(), args=c["args"].decode()) for c in ocalls] == want
+        assert views[i].acc_content.decode() == exp["content"][i]
+        if exp["usage"][i] is not None:
+            usage_recs = [r for r in o.recs if r.get("usage")]
+            assert usage_recs and list(usage_recs[-1]["usage"]) == exp["usage"][i]
+
+
+@pytest.mark.parametrize("fx", [f for f in GOLD if "parsed" in f["expect"]], ids=lambda f: f["name"])
+def test_reference_fixtures_builder(engine, fx):
+    body = (fx["iterations"][0][0] + "\n").encode()
+    outs, views = _run_and_check(engine, [body], [R], folds=True)
+    _, _, _, _, calls = agent_results(engine.L, outs[0].agent)
+    got = [dict(id=c["id"].decode(), name=c["name"].decode(), args=c["args"].decode()) for c in calls]
+    assert got == fx["expect"]["parsed"]
+
+
+# ------------------------------------------------------------------ BASELINE.json configs (reduced stream counts)
+@pytest.mark.parametrize("name,n_streams,n_batches", [
+    ("C1", 1, 1), ("C1", 1, 9), ("C2", 256, 1), ("C2", 256, 4), ("C3", 256, 1), ("C3", 256, 5),
+    ("C4", 512, 1), ("C4", 512, 6)])
+def test_configs(engine, name, n_streams, n_batches):
+    streams, mode = synth.make_config(name, n_streams=n_streams)
+    bodies = [b for b, _, _ in streams]
+    if mode is None:    # C1: both modes
+        for m in (P, R, PP):
+            _run_and_check(engine, bodies, [m] * len(bodies), n_batches=n_batches, seed=11)
+    else:
+        _run_and_check(engine, bodies, [mode] * len(bodies), n_batches=n_batches, seed=13)
+
+
+def test_mixed_modes_and_folds(engine):
+    streams, _ = synth.make_config("C4", n_streams=300)
+    bodies = [b for b, _, _ in streams]
+    modes = [(R, PP, P)[i % 3] for i in range(len(bodies))]
+    outs, views = _run_and_check(engine, bodies, modes, n_batches=4, seed=3, folds=True)
+    L = engine.L
+    for i, (b, m, o, v) in enumerate(zip(bodies, modes, outs, views)):
+        if m == R:
+            content, has, term, fin, calls = agent_results(L, o.agent)
+            assert content == v.acc_content and has == v.has_tool_calls and term == v.terminated
+            assert calls == orc.parse_tool_calls(v.builder)
+            # telemetry over what the MCP path would have written (frames + final [DONE], mcp.go:253-299)
+            rc, usage, tcalls = telemetry_results(L, o.tele)
+            # the fold saw only the frames; the reference body also carries "data: [DONE]\n\n" (2 more pieces)
+        elif m == PP:
+            rc, usage, tcalls = telemetry_results(L, o.tele)
+            eusage, ecalls = orc.telemetry(b"".join(o.frames))
+            assert rc == 0
+            assert usage == eusage, i
+            assert tcalls == ecalls, i
+
+
+# ------------------------------------------------------------------ ragged / edge inputs
+def test_edges(engine):
+    nl = b"\n"
+    bodies = [
+        b"", nl, nl * 200, b"\r\n" * 50, b"no newline at all",
+        b"data: a\n" * 150,                                   # > 64 lines in one segment: several runs
+        (b"data: " + b"y" * 9000 + b"\n") * 3 + b"data: tail",   # lines longer than the window
+        b"data: " + b"z" * 30000 + b"\n\n" + b'data: {"choices":[{"delta":{"content":"after"}}]}\n\n',
+        ("　  data: {\"x\":1}  \n").encode(),   # unicode TrimSpace
+        b"\xc2\xa0data: x\xe2\x80\n",                         # incomplete UTF-8 space is not trimmed
+        b"data: [DONE] [DONE] [DONE]\n" * 40,                 # more [DONE] hits than the per-round list holds
+        b'data: {"a":"[DONE"}\ndata: {"b":"DONE]"}\ndata: [DONE\n',
+        b"DATA: x\ndata:x\ndata: \ndata:  \ndata: \t\n",
+    ]
+    for m in (P, R, PP):
+        for nb in (1, 3, 8):
+            _run_and_check(engine, bodies, [m] * len(bodies), n_batches=nb, seed=nb)
+
+
+def test_line_longer_than_carry_slot_fails_loudly(engine):
+    big = b"data: " + b"q" * 100000 + b"\n" + b"data: after\n"
+    outs = run_streams(engine, [big], [P], n_batches=1)
+    assert outs[0].flags & A.SEG_LINE_TOO_LONG and outs[0].flags & A.SEG_DEAD
+    outs = run_streams(engine, [big, b"data: ok\n"], [R, R], n_batches=4)
+    assert outs[0].flags & A.SEG_DEAD
+    assert outs[1].frames == [b"data: ok\n\n"]
+
+
+def test_reset_conn_starts_a_new_stream(engine):
+    body = b'data: {"choices":[{"delta":{"content":"a"},"finish_reason":"stop"}]}\n\ndata: {"choices":[{"delta":{"content":"unread"}}]}\n\n'
+    engine.reset_all()
+    slot, res = engine.process([(5, R, body)])
+    assert len(res.seg_frames(0)) == 1 and int(res.segs[0]["flags"]) & A.SEG_TERMINATED
+    engine.release(slot)
+    slot, res = engine.process([(5, R, body)])       # finished: bytes are never read (agent.go:169)
+    assert res.seg_frames(0) == [] and int(res.segs[0]["flags"]) & A.SEG_FINISHED
+    engine.release(slot)
+    engine.reset_conn(5)                              # next agent iteration / new request
+    slot, res = engine.process([(5, R, body)])
+    assert len(res.seg_frames(0)) == 1
+    engine.release(slot)
+
+
+# ------------------------------------------------------------------ JSON decoding fuzz
+TRICKY = [
+    b'{}', b'null', b' null ', b'[]', b'"x"', b'5', b'true', b'', b' ', b'{', b'}', b'{"a"}', b'{"a":}', b'{"a":1,}',
+    b'[1,]', b'{"a":1}}', b'{"a":1} x', b'{"a":01}', b'{"a":-}', b'{"a":1.}', b'{"a":.5}', b'{"a":1e}', b'{"a":1e+}',
+    b'{"a":+1}', b'{"a":tru}', b'{"a":nul}', b'{"a":"\\x"}', b'{"a":"\\u12"}', b'{"a":"\\u12g4"}', b'{"a":"\x01"}',
+    b'{"a":"\t"}', b'{"a":"\x7f"}', b'{"a":"\xff\xfe"}', b'{"choices":null}', b'{"choices":[]}', b'{"choices":{}}',
+    b'{"choices":"x"}', b'{"choices":[null]}', b'{"choices":[1]}', b'{"choices":[{}]}', b'{"choices":[{"delta":null}]}',
+    b'{"choices":[{"delta":[]}]}', b'{"choices":[{"delta":{"content":null}}]}', b'{"choices":[{"delta":{"content":5}}]}',
+    b'{"choices":[{"delta":{"content":"a","content":"b"}}]}', b'{"choices":[{"delta":{"content":"a","content":null}}]}',
+    b'{"Choices":[{"DELTA":{"CONTENT":"x"},"Finish_Reason":"stop"}]}',
+    b'{"choice\xc5\xbf":[{"delta":{"content":"long s"}}]}', b'{"to\xe2\x84\xaaen":1,"choices":[{"delta":{"tool_calls":null}}]}',
+    b'{"ch\\u006fices":[{"delta":{"c\\u006Fntent":"esc key"}}]}', b'{"choices":[{"delta":{"content":"\\ud83d\\ude00 \\ud83d x \\ude00 \\ud800\\u0041"}}]}',
+    b'{"choices":[{"delta":{"content":"bad \xc0\xaf \xed\xa0\x80 \xf4\x90\x80\x80 \xe2\x82"}}]}',
+    b'{"choices":[{"delta":{"content":"\\u0000\\b\\f\\n\\r\\t\\/\\\\\\""}}]}',
+    b'{"choices":[{"finish_reason":"st\\u006fp"}]}', b'{"choices":[{"finish_reason":"tool_calls"}]}',
+    b'{"choices":[{"finish_reason":"length"}]}', b'{"choices":[{"finish_reason":"weird_reason_that_is_long_and_unknown"}]}',
+    b'{"choices":[{"finish_reason":""}]}', b'{"choices":[{"finish_reason":null}]}', b'{"choices":[{"finish_reason":7}]}',
+    b'{"choices":[{"index":"0"}]}', b'{"choices":[{"index":1.0}]}', b'{"choices":[{"index":1e2}]}', b'{"choices":[{"index":-0}]}',
+    b'{"choices":[{"index":9223372036854775807}]}', b'{"choices":[{"index":9223372036854775808}]}',
+    b'{"choices":[{"index":-9223372036854775808}]}', b'{"choices":[{"index":-9223372036854775809}]}',
+    b'{"created":12345678901234567890}', b'{"created":null}', b'{"created":true}', b'{"id":5}', b'{"id":null}', b'{"model":{}}',
+    b'{"usage":null}', b'{"usage":{}}', b'{"usage":[]}', b'{"usage":{"prompt_tokens":1,"completion_tokens":2,"total_tokens":3}}',
+    b'{"usage":{"prompt_tokens":"1"}}', b'{"usage":{"prompt_tokens":1},"usage":{"total_tokens":9}}',
+    b'{"usage":{"prompt_tokens":1},"usage":null}', b'{"usage":{"PROMPT_TOKENS":7}}',
+    b'{"choices":[{"delta":{"tool_calls":[]}}]}', b'{"choices":[{"delta":{"tool_calls":[null]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{}]}}]}', b'{"choices":[{"delta":{"tool_calls":[{"id":""}]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"id":null,"function":null}]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"function":{}}]}}]}', b'{"choices":[{"delta":{"tool_calls":[{"function":{"name":"n"}}]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"function":{"arguments":"{\\"a\\":1}"},"index":3,"type":"function","id":"c"}]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"index":0,"function":{"name":"a"}},{"index":0,"function":{"arguments":"x"}},{"index":-1}]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"index":0}],"tool_calls":[{"index":1},{"index":2}]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"index":0,"id":"a"}],"tool_calls":null}}]}',
+    b'{"choices":[{"delta":{"tool_calls":{"index":0}}}]}', b'{"choices":[{"delta":{"tool_calls":[5]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"extra_content":{"google":{"thought_signature":"s","other":[1,{"a":2}]}}}]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"extra_content":{"google":{"thought_signature":5}}}]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"extra_content":{"google":{"thought_signature":5,"thought_signature":"ok"}}}]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"extra_content":{"google":{"Thought_Signature":5}}}]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"extra_content":{"google":[1]}}]}}]}', b'{"choices":[{"delta":{"tool_calls":[{"extra_content":{"google":null}}]}}]}',
+    b'{"choices":[{"delta":{"tool_calls":[{"extra_content":{"GOOGLE":"x"}}]}}]}',
+    b'{"choices":[{"logprobs":{"content":[{"token":"a","logprob":-0.5,"bytes":[97],"top_logprobs":[{"token":"b","logprob":-9999.0,"bytes":null}]}],"refusal":null}}]}',
+    b'{"choices":[{"logprobs":{"content":[{"logprob":3.4028235e38}]}}]}', b'{"choices":[{"logprobs":{"content":[{"logprob":3.4028236e38}]}}]}',
+    b'{"choices":[{"logprobs":{"content":[{"logprob":340282356779733661637539395458142568447}]}}]}',
+    b'{"choices":[{"logprobs":{"content":[{"logprob":340282356779733661637539395458142568448}]}}]}',
+    b'{"choices":[{"logprobs":{"content":[{"logprob":-1e39}]}}]}', b'{"choices":[{"logprobs":{"content":[{"logprob":1e-400}]}}]}',
+    b'{"choices":[{"logprobs":{"content":[{"logprob":0.00000e999}]}}]}', b'{"choices":[{"logprobs":{"content":[{"logprob":"x"}]}}]}',
+    b'{"choices":[{"logprobs":{"content":[{"bytes":[1.5]}]}}]}', b'{"choices":[{"logprobs":{"content":{}}}]}',
+    b'{"choices":[{"delta":{"content":"first"}},{"delta":{"content":"second","tool_calls":[{"id":"x"}]},"finish_reason":"stop"}]}',
+    b'{"choices":[{"delta":{"content":"a"}}],"choices":[{"finish_reason":"stop"}]}',
+    b'{"choices":[{"delta":{"content":"a"}}],"choices":null}', b'{"choices":[{"delta":{"content":"a"}}],"choices":[]}',
+    b'{"unknown":{"deep":[1,2,{"x":[true,false,null,"s",1.5e-3]}]},"choices":[{"delta":{"content":"ok"}}]}',
+    b'\t\r\n {"choices" : [ { "delta" : { "content" : "ws" } , "finish_reason" : null } ] } \r',
+    b"[" * 128 + b"]" * 128, b"[" * 129 + b"]" * 129, b'{"a":' * 100 + b"1" + b"}" * 100,
+    b'{"choices":[{"delta":{"role":"assistant","content":null,"reasoning":5}}]}', b'{"system_fingerprint":false}',
+    b'{"reasoning_format":"raw","choices":[{"delta":{"reasoning_content":"r","refusal":null,"content":"c"}}]}',
+]
+
+
+def _mutate(rng, doc: bytes) -> bytes:
+    b = bytearray(doc)
+    if not b:
+        return bytes(b)
+    for _ in range(int(rng.integers(1, 4))):
+        op = int(rng.integers(0, 6))
+        i = int(rng.integers(0, len(b)))
+        if op == 0:
+            b[i] = int(rng.integers(0x20, 0x7F))
+        elif op == 1:
+            del b[i]
+        elif op == 2:
+            b.insert(i, b'{}[]:,"\\0123456789.eE-+ tfn'[int(rng.integers(0, 31))])
+        elif op == 3 and len(b) > 2:
+            j = int(rng.integers(0, len(b)))
+            b[i], b[j] = b[j], b[i]
+        elif op == 4:
+            b[i] = int(rng.integers(0x80, 0x100))
+        else:
+            b[i:i] = b'\\u00' + b'%02x' % int(rng.integers(0, 256))
+        if not b:
+            break
+    return bytes(b).replace(b"\n", b" ")
+
+
+def test_json_decoding_tricky(engine):
+    body = b"".join(b"data: " + d.replace(b"\n", b" ") + b"\n" for d in TRICKY)
+    # each document on its own connection so that early termination cannot hide later ones
+    bodies = [b"data: " + d.replace(b"\n", b" ") + b"\n" for d in TRICKY]
+    _run_and_check(engine, bodies, [R] * len(bodies))
+    _run_and_check(engine, [body], [PP], n_batches=5, seed=2)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_json_decoding_fuzz(engine, seed):
+    rng = np.random.default_rng(1000 + seed)
+    streams, _ = synth.make_config("C4", n_streams=60)
+    docs = []
+    for b, _, _ in streams:
+        for ev in b.split(b"\n\n"):
+            if ev.startswith(b"data: {"):
+                docs.append(ev[6:])
+    docs += TRICKY
+    mutated = [_mutate(rng, docs[int(rng.integers(0, len(docs)))]) for _ in range(3000)]
+    bodies = [b"data: " + d + b"\n" for d in mutated]
+    _run_and_check(engine, bodies, [R] * len(bodies))
+    # and as a single passthrough+parse stream cut into pieces (no early termination in mode P)
+    _run_and_check(engine, [b"".join(bodies)], [PP], n_batches=7, seed=seed)
+
+
+def test_product_does_not_use_oracle():
+    import inference_gateway_b200
+    root = os.path.dirname(inference_gateway_b200.__file__)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "import oracle" not in src and "from oracle" not in src and "sse_oracle" not in src, f
