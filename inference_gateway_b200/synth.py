@@ -155,12 +155,13 @@ CONFIGS = {
 }
 
 
-def make_config(name: str, n_streams: int | None = None, n_content: int | None = None):
-    """Returns (list of (bytes, n_events, flavour), mode) for a BASELINE.json config."""
+def make_config(name: str, n_streams: int | None = None, n_content: int | None = None, shard: int = 0):
+    """Returns (list of (bytes, n_events, flavour), mode) for a BASELINE.json config.
+    shard > 0 derives an independent stream population for another GPU (seed + 0x1000 * shard)."""
     idx, n, mean, flavours, mode, tool_frac = CONFIGS[name]
     if n_streams is not None:
         n = n_streams
-    g = Synth(0xB200 + idx)
+    g = Synth(0xB200 + idx + 0x1000 * shard)
     out = []
     for i in range(n):
         fl = flavours[i % len(flavours)]
