@@ -186,7 +186,12 @@ def main():
     bodies, mode, n_events = build_workload(args.streams, rank, args.workload)
     in_payload = sum(map(len, bodies))
     eng = SseEngine(device=local_rank, max_conns=len(bodies), bytes_per_batch=in_payload, n_slots=2, carry_slot_bytes=16384)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: its handle is passed to the library so that the kernels, the resets and the
+    # CUDA events of the timed region all live on the same stream (handle 0 would mean "library stream")
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     slot, arena, segs = eng.acquire()
     n_segs, in_bytes, _ = fill_slot(eng, arena, segs, bodies, mode)

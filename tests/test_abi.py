@@ -1,0 +1,65 @@
+"""CPU: the C-ABI library loads, exports every symbol include/sse_gpu.h declares, has the documented struct
+layouts, and fails loudly without a CUDA device (no CPU fallback). No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from inference_gateway_b200 import _abi as A
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = open(os.path.join(ROOT, "include", "sse_gpu.h")).read()
+
+
+def declared_functions():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    return sorted(set(re.findall(r"\b(sse_[a-z_0-9]+)\s*\(", body)))
+
+
+def test_exports_every_declared_symbol():
+    L = A.load()
+    names = declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} is declared in include/sse_gpu.h but not exported by libssegpu.so"
+    assert set(names) == set(A.EXPORTS)
+    assert L.sse_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(A.Seg) == 16 and C.sizeof(A.Frame) == 8 and C.sizeof(A.Rec) == 32 and C.sizeof(A.Tc) == 48
+    assert C.sizeof(A.Usage) == 24 and C.sizeof(A.Run) == 20 and C.sizeof(A.SegResult) == 32
+    assert C.sizeof(A.Config) == 14 * 4
+    cfg = A.Config()
+    A.load().sse_default_config(C.byref(cfg), 1024, 1 << 20)
+    assert cfg.struct_size == C.sizeof(A.Config) and cfg.max_conns == 1024 and cfg.in_arena_bytes % 16 == 0
+
+
+def test_strerror_and_argument_checks():
+    L = A.load()
+    assert b"no CPU fallback" in L.sse_strerror(A.SSE_ERR_NO_DEVICE)
+    assert L.sse_strerror(0) == b"ok"
+    ctx = C.c_void_p()
+    bad = A.Config()
+    assert L.sse_init(0, C.byref(bad), C.byref(ctx)) == A.SSE_ERR_ARG        # struct_size mismatch
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from inference_gateway_b200 import SseEngine
+    with pytest.raises(A.SseError) as e:
+        SseEngine(device=0, max_conns=16, bytes_per_batch=1 << 16)
+    assert e.value.status == A.SSE_ERR_NO_DEVICE
+
+
+def test_sass_is_sm100a():
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", A.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
