@@ -64,8 +64,10 @@ typedef struct {
     uint32_t max_runs;         /* extra result runs per batch (segments with > 64 lines) */
     uint32_t carry_slot_bytes; /* per-connection held-back tail capacity == longest supported line */
     uint32_t n_slots;          /* batches in flight (pipeline depth), 1..8 */
-    uint32_t flags;            /* reserved, 0 */
+    uint32_t flags;            /* SSE_FLAG_* */
 } sse_config;
+
+#define SSE_FLAG_KERNEL_V1 1u  /* use the first-generation kernel (sequential per-lane decoder); default is v2 */
 
 /* One segment = the bytes read from ONE connection since the previous batch. in_off is 16-byte aligned. */
 typedef struct {

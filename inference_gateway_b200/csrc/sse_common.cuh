@@ -1,0 +1,733 @@
+// sse_common.cuh -- device helpers shared by the stream kernels: schema of the decoded document, strings.TrimSpace,
+// encoding/json pieces (string / number scanners, unquote, key folding), the sequential per-line decoder (v1 and
+// slow path of v2), run bookkeeping and the long-line path. Included by sse_kernel.cu and sse_kernel2.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "sse_device.cuh"
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 8;
+constexpr int BUF = 8192;          // line window per warp (bytes, multiple of 16)
+constexpr int LT_MAX = 64;         // lines per round
+constexpr int DONE_MAX = 16;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------- schema of the decoded document
+// providers/types/common_types.go:271-297 (tool-call chunk, function), :300-346 (choice, delta),
+// :349-371 (logprobs), :384-393 (usage), :451-478 (stream response), :686-698 + :835-862 (extra_content)
+enum : uint8_t { TY_SKIP, TY_STR, TY_PSTR, TY_INT, TY_F32, TY_STRUCT, TY_PSTRUCT, TY_SLICE, TY_PSLICE,
+                 TY_GOOGLE, TY_ROOT, TY_TS };
+enum : uint8_t { N_NONE = 0, N_ROOT, N_CHOICE, N_DELTA, N_TC, N_FUNC, N_EXTRA, N_USAGE, N_LOGPROBS, N_TOKLP,
+                 N_TOPLP, N_GOOGLE, A_CHOICES, A_TOOLCALLS, A_TOKLP, A_TOPLP, A_INTS, N_COUNT };
+enum : uint8_t { TG_NONE, TG_CHOICES, TG_USAGE, TG_PROMPT, TG_COMPLETION, TG_TOTAL, TG_FINISH, TG_CONTENT,
+                 TG_TOOLCALLS, TG_TC_ID, TG_TC_TYPE, TG_TC_INDEX, TG_TC_FUNCTION, TG_NAME, TG_ARGS };
+
+struct FieldDef { uint8_t len, ty, sub, tgt; char name[20]; };
+constexpr int N_FIELDS = 39;
+struct alignas(16) Schema { FieldDef f[N_FIELDS]; uint8_t first[N_COUNT]; uint8_t cnt[N_COUNT]; uint8_t pad[2]; };
+static_assert(sizeof(Schema) % 4 == 0, "schema is copied as 32-bit words");
+
+#define FD(nm, ty, sub, tgt) { (uint8_t)(sizeof(nm) - 1), ty, sub, tgt, nm }
+__constant__ Schema c_schema = {
+    {
+        /* N_ROOT (0..7) */
+        FD("choices", TY_SLICE, A_CHOICES, TG_CHOICES), FD("created", TY_INT, 0, 0), FD("id", TY_STR, 0, 0),
+        FD("model", TY_STR, 0, 0), FD("object", TY_STR, 0, 0), FD("reasoning_format", TY_PSTR, 0, 0),
+        FD("system_fingerprint", TY_PSTR, 0, 0), FD("usage", TY_PSTRUCT, N_USAGE, TG_USAGE),
+        /* N_CHOICE (8..11) */
+        FD("delta", TY_STRUCT, N_DELTA, 0), FD("finish_reason", TY_STR, 0, TG_FINISH), FD("index", TY_INT, 0, 0),
+        FD("logprobs", TY_PSTRUCT, N_LOGPROBS, 0),
+        /* N_DELTA (12..17) */
+        FD("content", TY_STR, 0, TG_CONTENT), FD("reasoning", TY_PSTR, 0, 0), FD("reasoning_content", TY_PSTR, 0, 0),
+        FD("refusal", TY_PSTR, 0, 0), FD("role", TY_STR, 0, 0), FD("tool_calls", TY_PSLICE, A_TOOLCALLS, TG_TOOLCALLS),
+        /* N_TC (18..22) */
+        FD("extra_content", TY_PSTRUCT, N_EXTRA, 0), FD("function", TY_PSTRUCT, N_FUNC, TG_TC_FUNCTION),
+        FD("id", TY_PSTR, 0, TG_TC_ID), FD("index", TY_INT, 0, TG_TC_INDEX), FD("type", TY_PSTR, 0, TG_TC_TYPE),
+        /* N_FUNC (23..24) */
+        FD("arguments", TY_STR, 0, TG_ARGS), FD("name", TY_STR, 0, TG_NAME),
+        /* N_EXTRA (25) */
+        FD("google", TY_GOOGLE, N_GOOGLE, 0),
+        /* N_USAGE (26..28) */
+        FD("completion_tokens", TY_INT, 0, TG_COMPLETION), FD("prompt_tokens", TY_INT, 0, TG_PROMPT),
+        FD("total_tokens", TY_INT, 0, TG_TOTAL),
+        /* N_LOGPROBS (29..30) */
+        FD("content", TY_SLICE, A_TOKLP, 0), FD("refusal", TY_SLICE, A_TOKLP, 0),
+        /* N_TOKLP (31..34) */
+        FD("bytes", TY_SLICE, A_INTS, 0), FD("logprob", TY_F32, 0, 0), FD("token", TY_STR, 0, 0),
+        FD("top_logprobs", TY_SLICE, A_TOPLP, 0),
+        /* N_TOPLP (35..37) */
+        FD("bytes", TY_SLICE, A_INTS, 0), FD("logprob", TY_F32, 0, 0), FD("token", TY_STR, 0, 0),
+        /* N_GOOGLE (38): exact (case-sensitive) map key, common_types.go:842 */
+        FD("thought_signature", TY_TS, 0, 0),
+    },
+    /* first */ { 0, 0, 8, 12, 18, 23, 25, 26, 29, 31, 35, 38, 0, 0, 0, 0, 0 },
+    /* cnt   */ { 0, 8, 4, 6, 5, 2, 1, 3, 2, 4, 3, 1, 0, 0, 0, 0, 0 },
+    { 0, 0 },
+};
+
+struct LineEnt {
+    uint16_t nl;        // window position of the terminating '\n'
+    uint16_t src_s;     // first source byte of the frame (mode P: line start; mode R: start of "data: ")
+    uint16_t pay_s;     // payload handed to the decoder [pay_s, pay_e)
+    uint16_t pay_e;
+    uint16_t flen;      // emitted frame length (0: nothing emitted)
+    uint8_t  kind;      // K_*
+    uint8_t  parse;     // 1: decode payload
+};
+enum : uint8_t { K_DROP = 0, K_EMIT = 1, K_DONE = 2, K_DONE_EXACT = 3 };
+
+struct WarpSmem {
+    alignas(16) uint8_t buf[BUF + 16];
+    LineEnt lt[LT_MAX];
+    uint16_t done_pos[DONE_MAX];
+    uint32_t done_cnt;
+    uint32_t pad[3];
+};
+
+struct CtaSmem {
+    Schema schema;
+    WarpSmem w[WARPS_PER_CTA];
+};
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// 4-bit mask of the bytes of w equal to the byte replicated in pat
+__device__ __forceinline__ uint32_t eqmask4(uint32_t w, uint32_t pat) {
+    uint32_t c = __vcmpeq4(w, pat) & 0x01010101u;
+    return ((c * 0x00204081u) >> 21) & 0xFu;
+}
+__device__ __forceinline__ uint32_t eqmask16(const uint4 &v, uint32_t pat) {
+    return eqmask4(v.x, pat) | (eqmask4(v.y, pat) << 4) | (eqmask4(v.z, pat) << 8) | (eqmask4(v.w, pat) << 12);
+}
+
+// ---------------------------------------------------------------- strings.TrimSpace pieces
+// unicode.IsSpace code points in UTF-8: ASCII \t\n\v\f\r ' ', U+0085, U+00A0, U+1680, U+2000-200A,
+// U+2028, U+2029, U+202F, U+205F, U+3000 (Go strings.TrimSpace / utf8.DecodeRune semantics).
+__device__ __forceinline__ int space_prefix(const uint8_t *s, int n) {
+    if (n <= 0) return 0;
+    uint32_t c = s[0];
+    if (c == ' ' || (c >= 0x09 && c <= 0x0D)) return 1;
+    if (c < 0x80) return 0;
+    if (n >= 2 && c == 0xC2 && (s[1] == 0x85 || s[1] == 0xA0)) return 2;
+    if (n >= 3) {
+        uint32_t c1 = s[1], c2 = s[2];
+        if (c == 0xE1 && c1 == 0x9A && c2 == 0x80) return 3;
+        if (c == 0xE2 && c1 == 0x80 && ((c2 >= 0x80 && c2 <= 0x8A) || c2 == 0xA8 || c2 == 0xA9 || c2 == 0xAF)) return 3;
+        if (c == 0xE2 && c1 == 0x81 && c2 == 0x9F) return 3;
+        if (c == 0xE3 && c1 == 0x80 && c2 == 0x80) return 3;
+    }
+    return 0;
+}
+__device__ __forceinline__ int space_suffix(const uint8_t *s, int n) {
+    if (n <= 0) return 0;
+    uint32_t c = s[n - 1];
+    if (c == ' ' || (c >= 0x09 && c <= 0x0D)) return 1;
+    if (c < 0x80) return 0;
+    if (n >= 2 && space_prefix(s + n - 2, 2) == 2) return 2;
+    if (n >= 3 && space_prefix(s + n - 3, 3) == 3) return 3;
+    return 0;
+}
+__device__ __forceinline__ void trim_space(const uint8_t *s, int &a, int &b) {
+    int k;
+    while (a < b && (k = space_prefix(s + a, b - a)) != 0) a += k;
+    while (b > a && (k = space_suffix(s + a, b - a)) != 0) b -= k;
+}
+__device__ __forceinline__ bool is_data_prefix(const uint8_t *s, int n) {
+    return n >= 6 && s[0] == 'd' && s[1] == 'a' && s[2] == 't' && s[3] == 'a' && s[4] == ':' && s[5] == ' ';
+}
+__device__ __forceinline__ bool is_done_at(const uint8_t *s) {   // "[DONE]"
+    return s[0] == '[' && s[1] == 'D' && s[2] == 'O' && s[3] == 'N' && s[4] == 'E' && s[5] == ']';
+}
+
+// ---------------------------------------------------------------- encoding/json pieces
+// utf8.DecodeRune acceptance: size of a valid sequence at s (n bytes available) or 0
+__device__ __forceinline__ int utf8_valid_len(const uint8_t *s, int n) {
+    uint32_t c = s[0];
+    if (c < 0x80) return 1;
+    if (c >= 0xC2 && c <= 0xDF) return (n >= 2 && (s[1] & 0xC0) == 0x80) ? 2 : 0;
+    if (c >= 0xE0 && c <= 0xEF) {
+        uint32_t lo = (c == 0xE0) ? 0xA0 : 0x80, hi = (c == 0xED) ? 0x9F : 0xBF;
+        return (n >= 3 && s[1] >= lo && s[1] <= hi && (s[2] & 0xC0) == 0x80) ? 3 : 0;
+    }
+    if (c >= 0xF0 && c <= 0xF4) {
+        uint32_t lo = (c == 0xF0) ? 0x90 : 0x80, hi = (c == 0xF4) ? 0x8F : 0xBF;
+        return (n >= 4 && s[1] >= lo && s[1] <= hi && (s[2] & 0xC0) == 0x80 && (s[3] & 0xC0) == 0x80) ? 4 : 0;
+    }
+    return 0;
+}
+__device__ __forceinline__ int hexval(uint32_t c) {
+    if (c >= '0' && c <= '9') return (int)c - '0';
+    c |= 0x20;
+    if (c >= 'a' && c <= 'f') return (int)c - 'a' + 10;
+    return -1;
+}
+__device__ __forceinline__ int hex4(const uint8_t *s) {
+    int a = hexval(s[0]), b = hexval(s[1]), c = hexval(s[2]), d = hexval(s[3]);
+    if ((a | b | c | d) < 0) return -1;
+    return (a << 12) | (b << 8) | (c << 4) | d;
+}
+// Scan a string literal; p at the opening quote. Returns the position after the closing quote or -1.
+// esc: a backslash was seen; bad: invalid UTF-8 was seen (Go replaces it with U+FFFD when unquoting).
+__device__ int scan_string(const uint8_t *sm, int p, int pe, bool &esc, bool &bad) {
+    p++;
+    while (p < pe) {
+        uint32_t c = sm[p];
+        if (c == '"') return p + 1;
+        if (c < 0x20) return -1;
+        if (c == '\\') {
+            esc = true;
+            if (p + 1 >= pe) return -1;
+            uint32_t e = sm[p + 1];
+            if (e == 'u') {
+                if (p + 6 > pe || hex4(sm + p + 2) < 0) return -1;
+                p += 6;
+            } else if (e == '"' || e == '\\' || e == '/' || e == 'b' || e == 'f' || e == 'n' || e == 'r' || e == 't') {
+                p += 2;
+            } else return -1;
+            continue;
+        }
+        if (c >= 0x80) {
+            int k = utf8_valid_len(sm + p, pe - p);
+            if (k == 0) { bad = true; p++; } else p += k;
+            continue;
+        }
+        p++;
+    }
+    return -1;
+}
+// Scan a number literal. Returns end or -1. is_int: no fraction / exponent.
+__device__ int scan_number(const uint8_t *sm, int p, int pe, bool &is_int) {
+    is_int = true;
+    if (p < pe && sm[p] == '-') p++;
+    if (p >= pe) return -1;
+    uint32_t c = sm[p];
+    if (c == '0') p++;
+    else if (c >= '1' && c <= '9') { while (p < pe && (uint32_t)(sm[p] - '0') <= 9u) p++; }
+    else return -1;
+    if (p < pe && sm[p] == '.') {
+        is_int = false;
+        p++;
+        if (p >= pe || (uint32_t)(sm[p] - '0') > 9u) return -1;
+        while (p < pe && (uint32_t)(sm[p] - '0') <= 9u) p++;
+    }
+    if (p < pe && (sm[p] == 'e' || sm[p] == 'E')) {
+        is_int = false;
+        p++;
+        if (p < pe && (sm[p] == '+' || sm[p] == '-')) p++;
+        if (p >= pe || (uint32_t)(sm[p] - '0') > 9u) return -1;
+        while (p < pe && (uint32_t)(sm[p] - '0') <= 9u) p++;
+    }
+    return p;
+}
+// strconv.ParseInt(s, 10, 64) on an integer literal [s, e)
+__device__ bool parse_i64(const uint8_t *sm, int s, int e, int64_t &out) {
+    bool neg = false;
+    if (sm[s] == '-') { neg = true; s++; }
+    unsigned long long v = 0;
+    for (; s < e; s++) {
+        unsigned long long d = (unsigned long long)(sm[s] - '0');
+        if (v > (0xFFFFFFFFFFFFFFFFull - d) / 10ull) return false;
+        v = v * 10ull + d;
+    }
+    if (neg) { if (v > 0x8000000000000000ull) return false; out = (int64_t)(0ull - v); }
+    else { if (v > 0x7FFFFFFFFFFFFFFFull) return false; out = (int64_t)v; }
+    return true;
+}
+// strconv.ParseFloat(s, 32) range error: |x| >= 2^128 - 2^103 (exact decimal comparison)
+__device__ bool f32_overflows(const uint8_t *sm, int s, int e) {
+    const char *H = "340282356779733661637539395458142568448";   // 39 digits
+    if (s < e && sm[s] == '-') s++;
+    long long dexp = 0;
+    bool seen = false;
+    int cmp = 0, nd = 0;   // cmp: sign of (digits so far) vs H prefix
+    auto feed = [&](uint32_t c) {
+        if (nd < 39 && cmp == 0) { char h = H[nd]; cmp = ((char)c > h) - ((char)c < h); }
+        nd++;
+    };
+    int i = s;
+    for (; i < e && (uint32_t)(sm[i] - '0') <= 9u; i++) {
+        if (sm[i] != '0' || seen) { seen = true; feed(sm[i]); dexp++; }
+    }
+    if (i < e && sm[i] == '.') {
+        for (i++; i < e && (uint32_t)(sm[i] - '0') <= 9u; i++) {
+            if (sm[i] != '0' || seen) { seen = true; feed(sm[i]); } else dexp--;
+        }
+    }
+    if (!seen) return false;
+    if (i < e && (sm[i] == 'e' || sm[i] == 'E')) {
+        bool eneg = false; long long ex = 0;
+        i++;
+        if (i < e && (sm[i] == '+' || sm[i] == '-')) { eneg = sm[i] == '-'; i++; }
+        for (; i < e; i++) if (ex < 100000000) ex = ex * 10 + (sm[i] - '0');
+        dexp += eneg ? -ex : ex;
+    }
+    if (dexp > 39) return true;
+    if (dexp < 39) return false;
+    if (cmp != 0) return cmp > 0;
+    // all compared digits equal: remaining H digits vs implicit zeros
+    for (int k = nd; k < 39; k++) if (H[k] != '0') return false;
+    return true;   // >= H
+}
+__device__ __forceinline__ uint32_t put_rune(uint8_t *dst, uint32_t n, uint32_t r) {
+    if (r < 0x80) { if (dst) dst[n] = (uint8_t)r; return 1; }
+    if (r < 0x800) { if (dst) { dst[n] = 0xC0 | (r >> 6); dst[n + 1] = 0x80 | (r & 0x3F); } return 2; }
+    if (r < 0x10000) {
+        if (dst) { dst[n] = 0xE0 | (r >> 12); dst[n + 1] = 0x80 | ((r >> 6) & 0x3F); dst[n + 2] = 0x80 | (r & 0x3F); }
+        return 3;
+    }
+    if (dst) { dst[n] = 0xF0 | (r >> 18); dst[n + 1] = 0x80 | ((r >> 12) & 0x3F); dst[n + 2] = 0x80 | ((r >> 6) & 0x3F); dst[n + 3] = 0x80 | (r & 0x3F); }
+    return 4;
+}
+// decode.go unquoteBytes over a validated string body [s, e). dst == nullptr: count only. cap: stop at cap bytes.
+__device__ uint32_t json_unquote(const uint8_t *sm, int s, int e, uint8_t *dst, uint32_t cap) {
+    uint32_t n = 0;
+    int i = s;
+    while (i < e && n + 4 <= cap) {
+        uint32_t c = sm[i];
+        if (c == '\\') {
+            uint32_t esc = sm[i + 1];
+            i += 2;
+            uint32_t r;
+            switch (esc) {
+            case 'b': r = 8; break;
+            case 'f': r = 12; break;
+            case 'n': r = 10; break;
+            case 'r': r = 13; break;
+            case 't': r = 9; break;
+            case 'u': {
+                r = (uint32_t)hex4(sm + i);
+                i += 4;
+                if (r >= 0xD800 && r < 0xE000) {
+                    int r1 = -1;
+                    if (i + 6 <= e && sm[i] == '\\' && sm[i + 1] == 'u') r1 = hex4(sm + i + 2);
+                    if (r < 0xDC00 && r1 >= 0xDC00 && r1 < 0xE000) { r = 0x10000 + ((r - 0xD800) << 10) + ((uint32_t)r1 - 0xDC00); i += 6; }
+                    else r = 0xFFFD;
+                }
+                break;
+            }
+            default: r = esc; break;   // '"', '\\', '/'
+            }
+            n += put_rune(dst, n, r);
+        } else if (c < 0x80) {
+            if (dst) dst[n] = (uint8_t)c;
+            n++; i++;
+        } else {
+            int k = utf8_valid_len(sm + i, e - i);
+            if (k == 0) { n += put_rune(dst, n, 0xFFFD); i++; }
+            else { if (dst) for (int q = 0; q < k; q++) dst[n + q] = sm[i + q]; n += k; i += k; }
+        }
+    }
+    if (i < e) return cap + 1;   // did not fit
+    return n;
+}
+// encoding/json foldName equality (Go >= 1.21): ASCII case-insensitive, U+212A == 'k', U+017F == 's'
+__device__ bool key_eq(const uint8_t *k, int n, const char *name, int m, bool fold) {
+    if (!fold) {
+        if (n != m) return false;
+        for (int i = 0; i < n; i++) if (k[i] != (uint8_t)name[i]) return false;
+        return true;
+    }
+    int i = 0, q = 0;
+    while (i < n) {
+        uint32_t c = k[i];
+        if (c < 0x80) { if (c >= 'A' && c <= 'Z') c += 32; i++; }
+        else if (i + 1 < n && c == 0xC5 && k[i + 1] == 0xBF) { c = 's'; i += 2; }
+        else if (i + 2 < n && c == 0xE2 && k[i + 1] == 0x84 && k[i + 2] == 0xAA) { c = 'k'; i += 3; }
+        else return false;
+        if (q >= m || c != (uint8_t)name[q]) return false;
+        q++;
+    }
+    return q == m;
+}
+__device__ int match_field(const Schema &S, int node, const uint8_t *k, int n) {
+    int first = S.first[node], cnt = S.cnt[node];
+    bool fold = node != N_GOOGLE;
+    for (int f = first; f < first + cnt; f++)
+        if (key_eq(k, n, S.f[f].name, S.f[f].len, fold)) return f;
+    return -1;
+}
+__device__ uint32_t classify_finish(const uint8_t *s, int n) {
+    if (n == 0) return SSE_FIN_NONE;
+    if (key_eq(s, n, "stop", 4, false)) return SSE_FIN_STOP;
+    if (key_eq(s, n, "tool_calls", 10, false)) return SSE_FIN_TOOL_CALLS;
+    if (key_eq(s, n, "length", 6, false)) return SSE_FIN_LENGTH;
+    if (key_eq(s, n, "content_filter", 14, false)) return SSE_FIN_CONTENT_FILTER;
+    if (key_eq(s, n, "function_call", 13, false)) return SSE_FIN_FUNCTION_CALL;
+    return SSE_FIN_OTHER;
+}
+
+// ---------------------------------------------------------------- the decoder (one lane per line)
+struct ParseCtx {
+    const uint8_t *sm;     // warp window
+    const KParams *P;
+    const Schema *S;
+    bool emitted;          // string spans may point into the out arena
+    int64_t out_delta;     // out_off = out_delta + window position
+};
+struct Span { uint32_t off, len; bool text; };
+
+__device__ Span capture(const ParseCtx &cx, int s, int e, bool needs_decode) {
+    Span r;
+    if (!needs_decode && cx.emitted) { r.off = (uint32_t)(cx.out_delta + s); r.len = (uint32_t)(e - s); r.text = false; return r; }
+    uint32_t n = needs_decode ? json_unquote(cx.sm, s, e, nullptr, 0x7FFFFFF0u) : (uint32_t)(e - s);
+    r.text = true; r.len = n; r.off = 0;
+    if (n == 0) return r;
+    uint32_t o = atomicAdd(&cx.P->ctr->text_bytes, n);
+    if (o + n > cx.P->cap_text) { atomicExch(&cx.P->ctr->status, (int)SSE_ERR_OVERFLOW); r.len = 0; return r; }
+    r.off = o;
+    if (needs_decode) json_unquote(cx.sm, s, e, cx.P->text + o, 0x7FFFFFF0u);
+    else for (int i = s; i < e; i++) cx.P->text[o + (i - s)] = cx.sm[i];
+    return r;
+}
+
+struct PendingTc {
+    int64_t index;
+    uint32_t flags;            // SSE_TC_HAS_*
+    uint32_t id, type, name, args;   // packed (s << 16) | e window spans
+    uint32_t dec;              // bit0 id, bit1 type, bit2 name, bit3 args need unquoting
+};
+
+struct ParseOut {
+    uint32_t flags;
+    uint32_t content_off, content_len;
+    uint32_t tc_first, tc_count, n_choices, usage;
+};
+
+__device__ void flush_tc(const ParseCtx &cx, PendingTc &t, uint32_t &tc_first, uint32_t &tc_prev, bool &tc_valid) {
+    auto cap = [&](uint32_t sp, bool dec) { return capture(cx, (int)(sp >> 16), (int)(sp & 0xFFFF), dec); };
+    Span id = cap(t.id, t.dec & 1), ty = cap(t.type, t.dec & 2), nm = cap(t.name, t.dec & 4), ar = cap(t.args, t.dec & 8);
+    if ((t.flags & SSE_TC_HAS_ID) || ((t.flags & SSE_TC_HAS_FUNC) && (nm.len || ar.len))) tc_valid = true;
+    uint32_t idx = atomicAdd(&cx.P->ctr->n_tcs, 1u);
+    if (idx >= cx.P->cap_tcs) { atomicExch(&cx.P->ctr->status, (int)SSE_ERR_OVERFLOW); return; }
+    sse_tc o;
+    o.index = t.index;
+    o.flags = t.flags | (id.text ? SSE_TC_ID_TEXT : 0) | (ty.text ? SSE_TC_TYPE_TEXT : 0) |
+              (nm.text ? SSE_TC_NAME_TEXT : 0) | (ar.text ? SSE_TC_ARGS_TEXT : 0);
+    o.next = SSE_NONE;
+    o.id_off = id.off; o.id_len = id.len; o.type_off = ty.off; o.type_len = ty.len;
+    o.name_off = nm.off; o.name_len = nm.len; o.args_off = ar.off; o.args_len = ar.len;
+    cx.P->tcs[idx] = o;
+    if (tc_first == SSE_NONE) tc_first = idx; else cx.P->tcs[tc_prev].next = idx;
+    tc_prev = idx;
+}
+
+enum : int { ST_VALUE, ST_OBJ_FIRST, ST_OBJ_KEY, ST_COLON, ST_AFTER, ST_ARR_FIRST, ST_END };
+
+// json.Unmarshal(payload, &CreateChatCompletionStreamResponse) + the reads of agent.go:205-242.
+// Single pass: syntax (scanner.go), type compatibility (decode.go literalStore/object/array) and extraction.
+__device__ void decode_chunk(const ParseCtx &cx, int p, int pe, ParseOut &out) {
+    const uint8_t *sm = cx.sm;
+    const Schema &S = *cx.S;
+    int state = ST_VALUE, depth = 0, skip = 0, sd = 0;
+    unsigned long long ct0 = 0, ct1 = 0, sstk = 0;
+    bool syn = false, type_err = false, depth_limit = false, google_bad = false;
+    uint32_t cur_ty = TY_ROOT, cur_sub = N_ROOT, cur_tgt = TG_NONE;
+    uint32_t choices_count = 0, n_choices = 0;
+    bool has_usage = false;
+    int64_t u_prompt = 0, u_completion = 0, u_total = 0;
+    uint32_t finish = SSE_FIN_NONE;
+    uint32_t content_sp = 0; bool content_dec = false;
+    bool tc_nonnil = false, tc_open = false, tc_valid = false;
+    uint32_t tc_count = 0, tc_first = SSE_NONE, tc_prev = SSE_NONE;
+    PendingTc tc; tc.index = 0; tc.flags = 0; tc.id = tc.type = tc.name = tc.args = 0; tc.dec = 0;
+
+#define LIVE() (sd >= 3 && ((sstk >> 10) & 31ull) == N_CHOICE && choices_count == 1)
+#define TOPNODE() ((uint32_t)((sstk >> (5 * (sd - 1))) & 31ull))
+#define FLUSH_TC() do { if (tc_open) { flush_tc(cx, tc, tc_first, tc_prev, tc_valid); tc_open = false; } } while (0)
+#define ELEM_BEGIN() do { \
+        if (skip > 0) { cur_ty = TY_SKIP; cur_tgt = TG_NONE; } \
+        else { \
+            uint32_t nd_ = TOPNODE(); cur_tgt = TG_NONE; \
+            if (nd_ == A_CHOICES) { choices_count++; cur_ty = TY_STRUCT; cur_sub = N_CHOICE; } \
+            else if (nd_ == A_TOOLCALLS) { \
+                cur_ty = TY_STRUCT; cur_sub = N_TC; \
+                if (LIVE()) { FLUSH_TC(); tc_open = true; tc_count++; tc.index = 0; tc.flags = 0; tc.id = tc.type = tc.name = tc.args = 0; tc.dec = 0; } \
+            } \
+            else if (nd_ == A_TOKLP) { cur_ty = TY_STRUCT; cur_sub = N_TOKLP; } \
+            else if (nd_ == A_TOPLP) { cur_ty = TY_STRUCT; cur_sub = N_TOPLP; } \
+            else { cur_ty = TY_INT; } \
+        } } while (0)
+
+    for (;;) {
+        while (p < pe) { uint32_t w = sm[p]; if (w == ' ' || w == '\t' || w == '\r' || w == '\n') p++; else break; }
+        if (p >= pe) { if (state != ST_END) syn = true; break; }
+        uint32_t c = sm[p];
+        bool do_value = false, do_close = false;
+        switch (state) {
+        case ST_END: syn = true; break;
+        case ST_COLON:
+            if (c != ':') { syn = true; break; }
+            p++; state = ST_VALUE; break;
+        case ST_OBJ_FIRST:
+            if (c == '}') { p++; do_close = true; break; }
+            /* fallthrough */
+        case ST_OBJ_KEY: {
+            if (c != '"') { syn = true; break; }
+            bool esc = false, bad = false;
+            int q = scan_string(sm, p, pe, esc, bad);
+            if (q < 0) { syn = true; break; }
+            cur_ty = TY_SKIP; cur_tgt = TG_NONE; cur_sub = N_NONE;
+            if (skip == 0) {
+                int node = (int)TOPNODE();
+                int ks = p + 1, ke = q - 1, f;
+                if (!esc && !bad) f = match_field(S, node, sm + ks, ke - ks);
+                else {
+                    uint8_t tmp[72];
+                    uint32_t n = json_unquote(sm, ks, ke, tmp, 64);
+                    f = (n <= 64) ? match_field(S, node, tmp, (int)n) : -1;
+                }
+                if (f >= 0) { cur_ty = S.f[f].ty; cur_sub = S.f[f].sub; cur_tgt = S.f[f].tgt; }
+            }
+            p = q; state = ST_COLON; break;
+        }
+        case ST_ARR_FIRST:
+            if (c == ']') { p++; do_close = true; break; }
+            ELEM_BEGIN();
+            do_value = true; break;
+        case ST_VALUE: do_value = true; break;
+        case ST_AFTER: {
+            bool is_arr = (depth <= 64) ? ((ct0 >> (depth - 1)) & 1ull) : ((ct1 >> (depth - 65)) & 1ull);
+            if (c == ',') {
+                p++;
+                if (is_arr) { ELEM_BEGIN(); state = ST_VALUE; } else state = ST_OBJ_KEY;
+            } else if (c == (is_arr ? (uint32_t)']' : (uint32_t)'}')) { p++; do_close = true; }
+            else syn = true;
+            break;
+        }
+        }
+        if (syn) break;
+        if (do_close) {
+            depth--;
+            if (skip > 0) skip--;
+            else {
+                uint32_t node = TOPNODE();
+                sd--;
+                if (node == A_CHOICES) n_choices = choices_count;
+                else if (node == A_TOOLCALLS) { if (LIVE()) FLUSH_TC(); }
+                else if (node == N_GOOGLE) { if (google_bad) type_err = true; }
+            }
+            state = depth == 0 ? ST_END : ST_AFTER;
+            continue;
+        }
+        if (!do_value) continue;
+        // ---- a value starts at p
+        if (c == '{' || c == '[') {
+            bool arr = c == '[';
+            if (depth >= 128) { depth_limit = true; syn = true; break; }
+            if (depth < 64) ct0 = (ct0 & ~(1ull << depth)) | ((unsigned long long)arr << depth);
+            else ct1 = (ct1 & ~(1ull << (depth - 64))) | ((unsigned long long)arr << (depth - 64));
+            depth++; p++;
+            if (skip > 0 || cur_ty == TY_SKIP) skip++;
+            else {
+                bool ok = arr ? (cur_ty == TY_SLICE || cur_ty == TY_PSLICE)
+                              : (cur_ty == TY_STRUCT || cur_ty == TY_PSTRUCT || cur_ty == TY_ROOT || cur_ty == TY_GOOGLE);
+                if (!ok) { if (cur_ty == TY_TS) google_bad = true; else type_err = true; skip++; }
+                else {
+                    bool live = LIVE();
+                    sstk = (sstk & ~(31ull << (5 * sd))) | ((unsigned long long)cur_sub << (5 * sd));
+                    sd++;
+                    if (cur_tgt == TG_USAGE) has_usage = true;
+                    else if (cur_tgt == TG_TC_FUNCTION) { if (live && tc_open) tc.flags |= SSE_TC_HAS_FUNC; }
+                    else if (cur_tgt == TG_CHOICES) choices_count = 0;
+                    else if (cur_tgt == TG_TOOLCALLS) {
+                        if (live) { tc_nonnil = true; tc_count = 0; tc_first = SSE_NONE; tc_prev = SSE_NONE; tc_open = false; tc_valid = false; }
+                    }
+                    if (cur_sub == N_GOOGLE) google_bad = false;
+                }
+            }
+            state = arr ? ST_ARR_FIRST : ST_OBJ_FIRST;
+            continue;
+        }
+        if (c == '"') {
+            bool esc = false, bad = false;
+            int q = scan_string(sm, p, pe, esc, bad);
+            if (q < 0) { syn = true; break; }
+            if (cur_ty == TY_STR || cur_ty == TY_PSTR) {
+                if (cur_tgt != TG_NONE && LIVE()) {
+                    uint32_t sp = ((uint32_t)(p + 1) << 16) | (uint32_t)(q - 1);
+                    bool dec = esc || bad;
+                    switch (cur_tgt) {
+                    case TG_CONTENT: content_sp = sp; content_dec = dec; break;
+                    case TG_FINISH:
+                        if (!dec) finish = classify_finish(sm + p + 1, q - p - 2);
+                        else {
+                            uint8_t tmp[40];
+                            uint32_t n = json_unquote(sm, p + 1, q - 1, tmp, 32);
+                            finish = (n <= 32) ? classify_finish(tmp, (int)n) : (uint32_t)SSE_FIN_OTHER;
+                        }
+                        break;
+                    case TG_TC_ID: if (tc_open) { tc.flags |= SSE_TC_HAS_ID; tc.id = sp; tc.dec = (tc.dec & ~1u) | (dec ? 1u : 0u); } break;
+                    case TG_TC_TYPE: if (tc_open) { tc.flags |= SSE_TC_HAS_TYPE; tc.type = sp; tc.dec = (tc.dec & ~2u) | (dec ? 2u : 0u); } break;
+                    case TG_NAME: if (tc_open) { tc.name = sp; tc.dec = (tc.dec & ~4u) | (dec ? 4u : 0u); } break;
+                    case TG_ARGS: if (tc_open) { tc.args = sp; tc.dec = (tc.dec & ~8u) | (dec ? 8u : 0u); } break;
+                    default: break;
+                    }
+                }
+            } else if (cur_ty == TY_TS) google_bad = false;
+            else if (cur_ty != TY_SKIP) type_err = true;
+            p = q;
+        } else if (c == '-' || (c >= '0' && c <= '9')) {
+            bool is_int;
+            int q = scan_number(sm, p, pe, is_int);
+            if (q < 0) { syn = true; break; }
+            if (cur_ty == TY_INT) {
+                int64_t v;
+                if (!is_int || !parse_i64(sm, p, q, v)) type_err = true;
+                else if (cur_tgt == TG_PROMPT) u_prompt = v;
+                else if (cur_tgt == TG_COMPLETION) u_completion = v;
+                else if (cur_tgt == TG_TOTAL) u_total = v;
+                else if (cur_tgt == TG_TC_INDEX) { if (tc_open && LIVE()) tc.index = v; }
+            } else if (cur_ty == TY_F32) { if (f32_overflows(sm, p, q)) type_err = true; }
+            else if (cur_ty == TY_TS) google_bad = true;
+            else if (cur_ty != TY_SKIP) type_err = true;
+            p = q;
+        } else if (c == 't') {
+            if (p + 4 > pe || sm[p + 1] != 'r' || sm[p + 2] != 'u' || sm[p + 3] != 'e') { syn = true; break; }
+            p += 4;
+            if (cur_ty == TY_TS) google_bad = true; else if (cur_ty != TY_SKIP) type_err = true;
+        } else if (c == 'f') {
+            if (p + 5 > pe || sm[p + 1] != 'a' || sm[p + 2] != 'l' || sm[p + 3] != 's' || sm[p + 4] != 'e') { syn = true; break; }
+            p += 5;
+            if (cur_ty == TY_TS) google_bad = true; else if (cur_ty != TY_SKIP) type_err = true;
+        } else if (c == 'n') {
+            if (p + 4 > pe || sm[p + 1] != 'u' || sm[p + 2] != 'l' || sm[p + 3] != 'l') { syn = true; break; }
+            p += 4;
+            // literalStore(null): pointers / slices -> nil, everything else untouched
+            if (cur_ty == TY_TS) google_bad = false;
+            else switch (cur_tgt) {
+            case TG_CHOICES:
+                n_choices = 0; choices_count = 0; finish = SSE_FIN_NONE; content_sp = 0; content_dec = false;
+                tc_nonnil = false; tc_open = false; tc_valid = false; tc_count = 0; tc_first = SSE_NONE; tc_prev = SSE_NONE;
+                break;
+            case TG_USAGE: has_usage = false; u_prompt = u_completion = u_total = 0; break;
+            case TG_TOOLCALLS:
+                if (LIVE()) { tc_nonnil = false; tc_open = false; tc_valid = false; tc_count = 0; tc_first = SSE_NONE; tc_prev = SSE_NONE; }
+                break;
+            case TG_TC_ID: if (tc_open && LIVE()) { tc.flags &= ~SSE_TC_HAS_ID; tc.id = 0; tc.dec &= ~1u; } break;
+            case TG_TC_TYPE: if (tc_open && LIVE()) { tc.flags &= ~SSE_TC_HAS_TYPE; tc.type = 0; tc.dec &= ~2u; } break;
+            case TG_TC_FUNCTION: if (tc_open && LIVE()) { tc.flags &= ~SSE_TC_HAS_FUNC; tc.name = tc.args = 0; tc.dec &= ~12u; } break;
+            default: break;
+            }
+        } else { syn = true; break; }
+        state = depth == 0 ? ST_END : ST_AFTER;
+    }
+#undef LIVE
+#undef TOPNODE
+#undef FLUSH_TC
+#undef ELEM_BEGIN
+
+    out.flags = 0; out.content_off = 0; out.content_len = 0;
+    out.tc_first = SSE_NONE; out.tc_count = 0; out.n_choices = 0; out.usage = SSE_NONE;
+    if (depth_limit) out.flags |= SSE_F_DEPTH_LIMIT;
+    if (syn || type_err) return;
+    out.flags |= SSE_F_JSON_OK;
+    out.n_choices = n_choices;
+    if (has_usage) {
+        uint32_t idx = atomicAdd(&cx.P->ctr->n_usages, 1u);
+        if (idx < cx.P->cap_usages) {
+            sse_usage u; u.prompt_tokens = u_prompt; u.completion_tokens = u_completion; u.total_tokens = u_total;
+            cx.P->usages[idx] = u;
+            out.usage = idx; out.flags |= SSE_F_HAS_USAGE;
+        } else atomicExch(&cx.P->ctr->status, (int)SSE_ERR_OVERFLOW);
+    }
+    if (n_choices > 0) {
+        Span ct = capture(cx, (int)(content_sp >> 16), (int)(content_sp & 0xFFFF), content_dec);
+        out.content_off = ct.len ? ct.off : 0; out.content_len = ct.len;
+        if (ct.text && ct.len) out.flags |= SSE_F_CONTENT_TEXT;
+        out.flags |= finish << SSE_F_FINISH_SHIFT;
+        if (tc_nonnil) out.flags |= SSE_F_TC_NONNIL;
+        if (tc_valid) out.flags |= SSE_F_TC_VALID;
+        out.tc_first = tc_count ? tc_first : SSE_NONE;
+        out.tc_count = tc_count;
+    }
+}
+
+// ---------------------------------------------------------------- warp-cooperative helpers
+// copy n bytes global -> shared so that they END at smem offset `end_off` (byte granularity)
+__device__ void copy_g2s_bytes(uint8_t *sm_dst, const uint8_t *g_src, int n) {
+    for (int i = lane_id(); i < n; i += 32) sm_dst[i] = g_src[i];
+}
+__device__ void copy_s2g_bytes(uint8_t *g_dst, const uint8_t *sm_src, int n) {
+    for (int i = lane_id(); i < n; i += 32) g_dst[i] = sm_src[i];
+}
+__device__ void copy_g2g_bytes(uint8_t *g_dst, const uint8_t *g_src, int n) {
+    for (int i = lane_id(); i < n; i += 32) g_dst[i] = g_src[i];
+}
+
+struct RunChain {           // lane-uniform bookkeeping of a segment's result runs
+    sse_run first;
+    bool have_first;
+    uint32_t last_idx;      // index in runs[] of the last appended run (SSE_NONE: the inline one)
+};
+
+__device__ void append_run(const KParams &P, RunChain &rc, uint32_t ff, uint32_t fc, uint32_t rf, uint32_t rcnt) {
+    if (fc == 0 && rcnt == 0) return;
+    if (!rc.have_first) {
+        rc.first.frame_first = ff; rc.first.frame_count = fc; rc.first.rec_first = rf; rc.first.rec_count = rcnt;
+        rc.first.next = SSE_NONE; rc.have_first = true; rc.last_idx = SSE_NONE;
+        return;
+    }
+    uint32_t idx = 0;
+    if (lane_id() == 0) idx = atomicAdd(&P.ctr->n_runs, 1u);
+    idx = __shfl_sync(FULL, idx, 0);
+    if (idx >= P.cap_runs) { if (lane_id() == 0) atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW); return; }
+    if (lane_id() == 0) {
+        sse_run r; r.frame_first = ff; r.frame_count = fc; r.rec_first = rf; r.rec_count = rcnt; r.next = SSE_NONE;
+        P.runs[idx] = r;
+        if (rc.last_idx != SSE_NONE) P.runs[rc.last_idx].next = idx;
+    }
+    if (rc.last_idx == SSE_NONE) rc.first.next = idx;
+    rc.last_idx = idx;
+}
+
+// A line that never fit the window, assembled in the connection's carry slot (HBM): classified and emitted
+// straight from global memory; its payload is not decoded (SSE_F_TOO_LONG).
+__device__ bool process_long_line(const KParams &P, RunChain &rc, const uint8_t *line, int L, uint32_t mode) {
+    const uint32_t lane = lane_id();
+    int a = 0, b = L;           // frame source [a, b) ; R: trimmed
+    bool emit = true, done = false, parse = false;
+    int flen = L;
+    if (mode & SSE_MODE_R) {
+        trim_space(line, a, b);   // every lane, from global (ends only)
+        bool found = false;
+        for (int i = a + (int)lane; i + 6 <= b; i += 32) if (is_done_at(line + i)) found = true;
+        done = __any_sync(FULL, found);
+        bool pref = is_data_prefix(line + a, b - a);
+        emit = !done && pref && (b - a) > 6;
+        flen = emit ? (b - a) + 2 : 0;
+        parse = emit || (done);
+    } else {
+        parse = (mode & SSE_MODE_PARSE) && is_data_prefix(line, L);
+    }
+    uint32_t nf = emit ? 1u : 0u, nr = parse ? 1u : 0u;
+    uint32_t ob = 0, fb = 0, rb = 0;
+    if (lane == 0) {
+        if (nf) { ob = atomicAdd(&P.ctr->out_bytes, (uint32_t)flen); fb = atomicAdd(&P.ctr->n_frames, 1u); }
+        if (nr) rb = atomicAdd(&P.ctr->n_recs, 1u);
+    }
+    ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0);
+    bool ovf = (nf && (ob + (uint32_t)flen > P.cap_out || fb >= P.cap_frames)) || (nr && rb >= P.cap_recs);
+    if (ovf) { if (lane == 0) atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW); return false; }
+    if (emit) {
+        if (mode & SSE_MODE_R) {
+            copy_g2g_bytes(P.out + ob, line + a, b - a);
+            if (lane < 2) P.out[ob + (uint32_t)(b - a) + lane] = '\n';
+        } else copy_g2g_bytes(P.out + ob, line, L);
+        if (lane == 0) { sse_frame f; f.off = ob; f.len = (uint32_t)flen; P.frames[fb] = f; }
+    }
+    if (parse && lane == 0) {
+        sse_rec r;
+        r.frame = emit ? fb : SSE_NONE;
+        r.flags = SSE_F_TOO_LONG | (done ? SSE_F_DONE_LINE : 0u);
+        r.content_off = r.content_len = 0; r.tc_first = SSE_NONE; r.tc_count = 0; r.n_choices = 0; r.usage = SSE_NONE;
+        r.payload_len = (uint32_t)((mode & SSE_MODE_R) ? (b - a) : L);
+        P.recs[rb] = r;
+    }
+    append_run(P, rc, fb, nf, rb, nr);
+    return true;
+}
+
+
+} // namespace

@@ -54,4 +54,6 @@ struct KParams {
 };
 
 // launch wrappers (sse_kernel.cu)
-int sse_launch_stream_kernel(const KParams &p, void *stream, int sm_count);
+int sse_launch_stream_kernel(const KParams &p, void *stream, int sm_count);            // v1: per-lane sequential decoder
+int sse_v2_prepare(int device);                                                        // builds + uploads the automaton tables
+int sse_launch_stream_kernel_v2(const KParams &p, void *stream, int sm_count, int device);

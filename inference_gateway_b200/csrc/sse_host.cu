@@ -110,7 +110,8 @@ int do_launch(sse_ctx *c, Slot &s, uint32_t n_segs, cudaStream_t st) {
     CU(cudaMemsetAsync(s.d_ctr, 0, sizeof(Counters), st));
     if (n_segs) {
         KParams p = make_params(c, s, n_segs);
-        int e = sse_launch_stream_kernel(p, (void *)st, c->sm_count);
+        int e = (c->cfg.flags & SSE_FLAG_KERNEL_V1) ? sse_launch_stream_kernel(p, (void *)st, c->sm_count)
+                                                    : sse_launch_stream_kernel_v2(p, (void *)st, c->sm_count, c->device);
         if (e != 0) { cu_ok((cudaError_t)e, "sse_stream_kernel launch"); return SSE_ERR_CUDA; }
         c->launches++;
     }
@@ -201,6 +202,10 @@ int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
     cudaDeviceProp prop;
     if (!cu_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete c; return SSE_ERR_CUDA; }
     c->sm_count = prop.multiProcessorCount;
+    if (!(cfg->flags & SSE_FLAG_KERNEL_V1)) {
+        int e2 = sse_v2_prepare(device);
+        if (e2 != 0) { cu_ok((cudaError_t)e2, "sse_v2_prepare"); delete c; return SSE_ERR_CUDA; }
+    }
     bool ok = true;
     ok = ok && cu_ok(cudaStreamCreateWithFlags(&c->ctl_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     ok = ok && cu_ok(cudaEventCreateWithFlags(&c->last_kernel, cudaEventDisableTiming), "cudaEventCreate");

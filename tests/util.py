@@ -26,7 +26,7 @@ def rec_to_dict(res, ri: int) -> dict:
     fl = int(r["flags"])
     d = dict(flags=fl, json_ok=bool(fl & A.F_JSON_OK), done=bool(fl & A.F_DONE_LINE),
              done_exact=bool(fl & A.F_DONE_EXACT), terminates=bool(fl & A.F_TERMINATES),
-             too_long=bool(fl & A.F_TOO_LONG), frame=int(r["frame"]), payload_len=int(r["payload_len"]))
+             too_long=bool(fl & (A.F_TOO_LONG | A.F_DEPTH_LIMIT)), frame=int(r["frame"]), payload_len=int(r["payload_len"]))
     if d["json_ok"]:
         d["n_choices"] = int(r["n_choices"])
         d["finish"] = (fl & A.F_FINISH_MASK) >> A.F_FINISH_SHIFT
