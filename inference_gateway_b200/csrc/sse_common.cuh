@@ -170,7 +170,7 @@ __device__ __forceinline__ int hex4(const uint8_t *s) {
 }
 // Scan a string literal; p at the opening quote. Returns the position after the closing quote or -1.
 // esc: a backslash was seen; bad: invalid UTF-8 was seen (Go replaces it with U+FFFD when unquoting).
-__device__ int scan_string(const uint8_t *sm, int p, int pe, bool &esc, bool &bad) {
+__device__ __noinline__ int scan_string(const uint8_t *sm, int p, int pe, bool &esc, bool &bad) {
     p++;
     while (p < pe) {
         uint32_t c = sm[p];
@@ -198,7 +198,7 @@ __device__ int scan_string(const uint8_t *sm, int p, int pe, bool &esc, bool &ba
     return -1;
 }
 // Scan a number literal. Returns end or -1. is_int: no fraction / exponent.
-__device__ int scan_number(const uint8_t *sm, int p, int pe, bool &is_int) {
+__device__ __noinline__ int scan_number(const uint8_t *sm, int p, int pe, bool &is_int) {
     is_int = true;
     if (p < pe && sm[p] == '-') p++;
     if (p >= pe) return -1;
@@ -222,7 +222,7 @@ __device__ int scan_number(const uint8_t *sm, int p, int pe, bool &is_int) {
     return p;
 }
 // strconv.ParseInt(s, 10, 64) on an integer literal [s, e)
-__device__ bool parse_i64(const uint8_t *sm, int s, int e, int64_t &out) {
+__device__ __noinline__ bool parse_i64(const uint8_t *sm, int s, int e, int64_t &out) {
     bool neg = false;
     if (sm[s] == '-') { neg = true; s++; }
     unsigned long long v = 0;
@@ -236,7 +236,7 @@ __device__ bool parse_i64(const uint8_t *sm, int s, int e, int64_t &out) {
     return true;
 }
 // strconv.ParseFloat(s, 32) range error: |x| >= 2^128 - 2^103 (exact decimal comparison)
-__device__ bool f32_overflows(const uint8_t *sm, int s, int e) {
+__device__ __noinline__ bool f32_overflows(const uint8_t *sm, int s, int e) {
     const char *H = "340282356779733661637539395458142568448";   // 39 digits
     if (s < e && sm[s] == '-') s++;
     long long dexp = 0;
@@ -281,7 +281,7 @@ __device__ __forceinline__ uint32_t put_rune(uint8_t *dst, uint32_t n, uint32_t 
     return 4;
 }
 // decode.go unquoteBytes over a validated string body [s, e). dst == nullptr: count only. cap: stop at cap bytes.
-__device__ uint32_t json_unquote(const uint8_t *sm, int s, int e, uint8_t *dst, uint32_t cap) {
+__device__ __noinline__ uint32_t json_unquote(const uint8_t *sm, int s, int e, uint8_t *dst, uint32_t cap) {
     uint32_t n = 0;
     int i = s;
     while (i < e && n + 4 <= cap) {
@@ -323,7 +323,7 @@ __device__ uint32_t json_unquote(const uint8_t *sm, int s, int e, uint8_t *dst, 
     return n;
 }
 // encoding/json foldName equality (Go >= 1.21): ASCII case-insensitive, U+212A == 'k', U+017F == 's'
-__device__ bool key_eq(const uint8_t *k, int n, const char *name, int m, bool fold) {
+__device__ __noinline__ bool key_eq(const uint8_t *k, int n, const char *name, int m, bool fold) {
     if (!fold) {
         if (n != m) return false;
         for (int i = 0; i < n; i++) if (k[i] != (uint8_t)name[i]) return false;
@@ -341,14 +341,14 @@ __device__ bool key_eq(const uint8_t *k, int n, const char *name, int m, bool fo
     }
     return q == m;
 }
-__device__ int match_field(const Schema &S, int node, const uint8_t *k, int n) {
+__device__ __noinline__ int match_field(const Schema &S, int node, const uint8_t *k, int n) {
     int first = S.first[node], cnt = S.cnt[node];
     bool fold = node != N_GOOGLE;
     for (int f = first; f < first + cnt; f++)
         if (key_eq(k, n, S.f[f].name, S.f[f].len, fold)) return f;
     return -1;
 }
-__device__ uint32_t classify_finish(const uint8_t *s, int n) {
+__device__ __noinline__ uint32_t classify_finish(const uint8_t *s, int n) {
     if (n == 0) return SSE_FIN_NONE;
     if (key_eq(s, n, "stop", 4, false)) return SSE_FIN_STOP;
     if (key_eq(s, n, "tool_calls", 10, false)) return SSE_FIN_TOOL_CALLS;
@@ -368,17 +368,20 @@ struct ParseCtx {
 };
 struct Span { uint32_t off, len; bool text; };
 
-__device__ Span capture(const ParseCtx &cx, int s, int e, bool needs_decode) {
+// dec: 0 = the raw bytes are the decoded string; 1 = has escapes; 2 (or 3) = may also hold invalid UTF-8, which
+// Go replaces by U+FFFD (1 byte -> 3). Decoding is single pass into a bound-sized text-arena allocation.
+__device__ __noinline__ Span capture(const ParseCtx &cx, int s, int e, int dec) {
     Span r;
-    if (!needs_decode && cx.emitted) { r.off = (uint32_t)(cx.out_delta + s); r.len = (uint32_t)(e - s); r.text = false; return r; }
-    uint32_t n = needs_decode ? json_unquote(cx.sm, s, e, nullptr, 0x7FFFFFF0u) : (uint32_t)(e - s);
-    r.text = true; r.len = n; r.off = 0;
-    if (n == 0) return r;
-    uint32_t o = atomicAdd(&cx.P->ctr->text_bytes, n);
-    if (o + n > cx.P->cap_text) { atomicExch(&cx.P->ctr->status, (int)SSE_ERR_OVERFLOW); r.len = 0; return r; }
+    if (!dec && cx.emitted) { r.off = (uint32_t)(cx.out_delta + s); r.len = (uint32_t)(e - s); r.text = false; return r; }
+    const uint32_t raw = (uint32_t)(e - s);
+    r.text = true; r.len = 0; r.off = 0;
+    if (raw == 0) return r;
+    const uint32_t bound = (dec & 2) ? 3u * raw : raw;
+    uint32_t o = atomicAdd(&cx.P->ctr->text_bytes, bound);
+    if (o + bound > cx.P->cap_text) { atomicExch(&cx.P->ctr->status, (int)SSE_ERR_OVERFLOW); return r; }
     r.off = o;
-    if (needs_decode) json_unquote(cx.sm, s, e, cx.P->text + o, 0x7FFFFFF0u);
-    else for (int i = s; i < e; i++) cx.P->text[o + (i - s)] = cx.sm[i];
+    if (dec) r.len = json_unquote(cx.sm, s, e, cx.P->text + o, 0x7FFFFFF0u);
+    else { for (int i = s; i < e; i++) cx.P->text[o + (i - s)] = cx.sm[i]; r.len = raw; }
     return r;
 }
 
@@ -395,8 +398,8 @@ struct ParseOut {
     uint32_t tc_first, tc_count, n_choices, usage;
 };
 
-__device__ void flush_tc(const ParseCtx &cx, PendingTc &t, uint32_t &tc_first, uint32_t &tc_prev, bool &tc_valid) {
-    auto cap = [&](uint32_t sp, bool dec) { return capture(cx, (int)(sp >> 16), (int)(sp & 0xFFFF), dec); };
+__device__ __noinline__ void flush_tc(const ParseCtx &cx, PendingTc &t, uint32_t &tc_first, uint32_t &tc_prev, bool &tc_valid) {
+    auto cap = [&](uint32_t sp, bool dec) { return capture(cx, (int)(sp >> 16), (int)(sp & 0xFFFF), dec ? 3 : 0); };
     Span id = cap(t.id, t.dec & 1), ty = cap(t.type, t.dec & 2), nm = cap(t.name, t.dec & 4), ar = cap(t.args, t.dec & 8);
     if ((t.flags & SSE_TC_HAS_ID) || ((t.flags & SSE_TC_HAS_FUNC) && (nm.len || ar.len))) tc_valid = true;
     uint32_t idx = atomicAdd(&cx.P->ctr->n_tcs, 1u);
@@ -417,7 +420,7 @@ enum : int { ST_VALUE, ST_OBJ_FIRST, ST_OBJ_KEY, ST_COLON, ST_AFTER, ST_ARR_FIRS
 
 // json.Unmarshal(payload, &CreateChatCompletionStreamResponse) + the reads of agent.go:205-242.
 // Single pass: syntax (scanner.go), type compatibility (decode.go literalStore/object/array) and extraction.
-__device__ void decode_chunk(const ParseCtx &cx, int p, int pe, ParseOut &out) {
+__device__ __noinline__ void decode_chunk(const ParseCtx &cx, int p, int pe, ParseOut &out) {
     const uint8_t *sm = cx.sm;
     const Schema &S = *cx.S;
     int state = ST_VALUE, depth = 0, skip = 0, sd = 0;
@@ -633,7 +636,7 @@ __device__ void decode_chunk(const ParseCtx &cx, int p, int pe, ParseOut &out) {
         } else atomicExch(&cx.P->ctr->status, (int)SSE_ERR_OVERFLOW);
     }
     if (n_choices > 0) {
-        Span ct = capture(cx, (int)(content_sp >> 16), (int)(content_sp & 0xFFFF), content_dec);
+        Span ct = capture(cx, (int)(content_sp >> 16), (int)(content_sp & 0xFFFF), content_dec ? 3 : 0);
         out.content_off = ct.len ? ct.off : 0; out.content_len = ct.len;
         if (ct.text && ct.len) out.flags |= SSE_F_CONTENT_TEXT;
         out.flags |= finish << SSE_F_FINISH_SHIFT;
@@ -662,7 +665,7 @@ struct RunChain {           // lane-uniform bookkeeping of a segment's result ru
     uint32_t last_idx;      // index in runs[] of the last appended run (SSE_NONE: the inline one)
 };
 
-__device__ void append_run(const KParams &P, RunChain &rc, uint32_t ff, uint32_t fc, uint32_t rf, uint32_t rcnt) {
+__device__ __noinline__ void append_run(const KParams &P, RunChain &rc, uint32_t ff, uint32_t fc, uint32_t rf, uint32_t rcnt) {
     if (fc == 0 && rcnt == 0) return;
     if (!rc.have_first) {
         rc.first.frame_first = ff; rc.first.frame_count = fc; rc.first.rec_first = rf; rc.first.rec_count = rcnt;
@@ -684,7 +687,7 @@ __device__ void append_run(const KParams &P, RunChain &rc, uint32_t ff, uint32_t
 
 // A line that never fit the window, assembled in the connection's carry slot (HBM): classified and emitted
 // straight from global memory; its payload is not decoded (SSE_F_TOO_LONG).
-__device__ bool process_long_line(const KParams &P, RunChain &rc, const uint8_t *line, int L, uint32_t mode) {
+__device__ __noinline__ bool process_long_line(const KParams &P, RunChain &rc, const uint8_t *line, int L, uint32_t mode) {
     const uint32_t lane = lane_id();
     int a = 0, b = L;           // frame source [a, b) ; R: trimmed
     bool emit = true, done = false, parse = false;

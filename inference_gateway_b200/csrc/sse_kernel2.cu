@@ -25,7 +25,8 @@ constexpr int V2_WARPS = 16;
 constexpr int V2_BUF = 6144;       // line window per warp
 constexpr int RING = 128;          // work items per warp
 constexpr int SEGSLOTS = 8;        // segments in flight per warp
-constexpr int STEPS = 16;          // automaton steps between refills
+constexpr int ROUNDS = 4;          // rounds between refills
+constexpr int KSTEPS = 4;          // plain automaton steps per round before the pending actions run
 
 struct SegSlot {
     unsigned long long term;       // min over terminating lines of (rec << 32 | frame); ~0ull: none
@@ -61,7 +62,7 @@ static_assert(sizeof(CtaSmem2) <= 227 * 1024, "shared memory budget");
 // per-string flags (cleared outside strings) and per-line flags
 constexpr uint32_t SF_ESC = 1, SF_HI = 2, SF_UPPER = 4, SF_BAD = 8, SF_STRMASK = 15;
 constexpr uint32_t SF_SYN = 0x100, SF_TYPE = 0x200, SF_DEPTH = 0x400, SF_GBAD = 0x800, SF_USAGE = 0x1000,
-                   SF_TCNONNIL = 0x2000, SF_TCOPEN = 0x4000, SF_TCVALID = 0x8000, SF_CDEC = 0x10000, SF_RMODE = 0x20000;
+                   SF_TCNONNIL = 0x2000, SF_TCOPEN = 0x4000, SF_TCVALID = 0x8000, SF_CDEC = 0x10000, SF_RMODE = 0x20000, SF_CBAD = 0x40000;
 
 struct Lane {
     uint32_t p, pe;                // out-arena offsets of the payload being decoded
@@ -73,6 +74,11 @@ struct Lane {
     bool busy;
 };
 
+// 0x80 in every byte of w that is '"', '\\', < 0x20 or >= 0x80 (exact for the lowest flagged byte)
+__device__ __forceinline__ uint32_t special_mask4(uint32_t w) {
+    const uint32_t q = w ^ 0x22222222u, b = w ^ 0x5C5C5C5Cu;
+    return (((q - 0x01010101u) & ~q) | ((b - 0x01010101u) & ~b) | ((w - 0x20202020u) & ~w) | w) & 0x80808080u;
+}
 __device__ __forceinline__ uint4 ldcg16(const uint8_t *base, uint32_t off) {
     return __ldcg(reinterpret_cast<const uint4 *>(base + (off & ~15u)));
 }
@@ -89,10 +95,10 @@ __device__ __forceinline__ void value_done(Lane &L) {
 
 __device__ void v2_flush_tc(const KParams &P, Lane &L, LaneScratch &S) {
     ParseCtx cx; cx.sm = P.out; cx.P = &P; cx.S = nullptr; cx.emitted = true; cx.out_delta = 0;
-    Span id = capture(cx, (int)S.id_off, (int)(S.id_off + S.id_len), S.tc_dec & 1);
-    Span ty = capture(cx, (int)S.type_off, (int)(S.type_off + S.type_len), S.tc_dec & 2);
-    Span nm = capture(cx, (int)S.name_off, (int)(S.name_off + S.name_len), S.tc_dec & 4);
-    Span ar = capture(cx, (int)S.args_off, (int)(S.args_off + S.args_len), S.tc_dec & 8);
+    Span id = capture(cx, (int)S.id_off, (int)(S.id_off + S.id_len), S.tc_dec & 3);
+    Span ty = capture(cx, (int)S.type_off, (int)(S.type_off + S.type_len), (S.tc_dec >> 2) & 3);
+    Span nm = capture(cx, (int)S.name_off, (int)(S.name_off + S.name_len), (S.tc_dec >> 4) & 3);
+    Span ar = capture(cx, (int)S.args_off, (int)(S.args_off + S.args_len), (S.tc_dec >> 6) & 3);
     if ((S.tc_flags & SSE_TC_HAS_ID) || ((S.tc_flags & SSE_TC_HAS_FUNC) && (nm.len || ar.len))) L.sf |= SF_TCVALID;
     L.sf &= ~SF_TCOPEN;
     uint32_t idx = atomicAdd(&P.ctr->n_tcs, 1u);
@@ -133,17 +139,17 @@ __device__ void v2_null(Lane &L, LaneScratch &S) {
     switch (tgt) {
     case TG_CHOICES:
         L.n_choices = 0; L.choices_count = 0; L.finish = SSE_FIN_NONE; L.content_off = L.content_len = 0;
-        L.sf &= ~(SF_CDEC | SF_TCNONNIL | SF_TCOPEN | SF_TCVALID);
+        L.sf &= ~(SF_CDEC | SF_CBAD | SF_TCNONNIL | SF_TCOPEN | SF_TCVALID);
         L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
         break;
     case TG_USAGE: L.sf &= ~SF_USAGE; S.u_prompt = S.u_completion = S.u_total = 0; break;
     case TG_TOOLCALLS:
         if (lane_live(L)) { L.sf &= ~(SF_TCNONNIL | SF_TCOPEN | SF_TCVALID); L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE; }
         break;
-    case TG_TC_ID: if ((L.sf & SF_TCOPEN) && lane_live(L)) { S.tc_flags &= ~SSE_TC_HAS_ID; S.id_off = S.id_len = 0; S.tc_dec &= ~1u; } break;
-    case TG_TC_TYPE: if ((L.sf & SF_TCOPEN) && lane_live(L)) { S.tc_flags &= ~SSE_TC_HAS_TYPE; S.type_off = S.type_len = 0; S.tc_dec &= ~2u; } break;
+    case TG_TC_ID: if ((L.sf & SF_TCOPEN) && lane_live(L)) { S.tc_flags &= ~SSE_TC_HAS_ID; S.id_off = S.id_len = 0; S.tc_dec &= ~3u; } break;
+    case TG_TC_TYPE: if ((L.sf & SF_TCOPEN) && lane_live(L)) { S.tc_flags &= ~SSE_TC_HAS_TYPE; S.type_off = S.type_len = 0; S.tc_dec &= ~12u; } break;
     case TG_TC_FUNCTION:
-        if ((L.sf & SF_TCOPEN) && lane_live(L)) { S.tc_flags &= ~SSE_TC_HAS_FUNC; S.name_off = S.name_len = S.args_off = S.args_len = 0; S.tc_dec &= ~12u; }
+        if ((L.sf & SF_TCOPEN) && lane_live(L)) { S.tc_flags &= ~SSE_TC_HAS_FUNC; S.name_off = S.name_len = S.args_off = S.args_len = 0; S.tc_dec &= ~0xF0u; }
         break;
     default: break;
     }
@@ -241,22 +247,25 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
         if (ty == TY_STR || ty == TY_PSTR) {
             if (tgt != TG_NONE && lane_live(L)) {
                 const uint32_t start = L.p - L.slen, len = L.slen;
-                const bool dec = (L.sf & (SF_ESC | SF_BAD)) != 0;
+                const uint32_t d2 = ((L.sf & SF_ESC) ? 1u : 0u) | ((L.sf & SF_BAD) ? 2u : 0u);
                 switch (tgt) {
-                case TG_CONTENT: L.content_off = start; L.content_len = len; L.sf = dec ? (L.sf | SF_CDEC) : (L.sf & ~SF_CDEC); break;
+                case TG_CONTENT:
+                    L.content_off = start; L.content_len = len;
+                    L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
+                    break;
                 case TG_FINISH:
                     if (len == 0) L.finish = SSE_FIN_NONE;
-                    else if (!dec) { uint32_t nm = T.accept[L.km]; uint32_t fv = nm != 0xFFu ? T.finmap[nm] : 0xFFu; L.finish = fv != 0xFFu ? fv : (uint32_t)SSE_FIN_OTHER; }
+                    else if (!d2) { uint32_t nm = T.accept[L.km]; uint32_t fv = nm != 0xFFu ? T.finmap[nm] : 0xFFu; L.finish = fv != 0xFFu ? fv : (uint32_t)SSE_FIN_OTHER; }
                     else {
                         uint8_t tmp[40];
                         uint32_t n = json_unquote(P.out, (int)start, (int)L.p, tmp, 32);
                         L.finish = (n <= 32) ? classify_finish(tmp, (int)n) : (uint32_t)SSE_FIN_OTHER;
                     }
                     break;
-                case TG_TC_ID: if (L.sf & SF_TCOPEN) { S.tc_flags |= SSE_TC_HAS_ID; S.id_off = start; S.id_len = len; S.tc_dec = (S.tc_dec & ~1u) | (dec ? 1u : 0u); } break;
-                case TG_TC_TYPE: if (L.sf & SF_TCOPEN) { S.tc_flags |= SSE_TC_HAS_TYPE; S.type_off = start; S.type_len = len; S.tc_dec = (S.tc_dec & ~2u) | (dec ? 2u : 0u); } break;
-                case TG_NAME: if (L.sf & SF_TCOPEN) { S.name_off = start; S.name_len = len; S.tc_dec = (S.tc_dec & ~4u) | (dec ? 4u : 0u); } break;
-                case TG_ARGS: if (L.sf & SF_TCOPEN) { S.args_off = start; S.args_len = len; S.tc_dec = (S.tc_dec & ~8u) | (dec ? 8u : 0u); } break;
+                case TG_TC_ID: if (L.sf & SF_TCOPEN) { S.tc_flags |= SSE_TC_HAS_ID; S.id_off = start; S.id_len = len; S.tc_dec = (S.tc_dec & ~3u) | d2; } break;
+                case TG_TC_TYPE: if (L.sf & SF_TCOPEN) { S.tc_flags |= SSE_TC_HAS_TYPE; S.type_off = start; S.type_len = len; S.tc_dec = (S.tc_dec & ~12u) | (d2 << 2); } break;
+                case TG_NAME: if (L.sf & SF_TCOPEN) { S.name_off = start; S.name_len = len; S.tc_dec = (S.tc_dec & ~0x30u) | (d2 << 4); } break;
+                case TG_ARGS: if (L.sf & SF_TCOPEN) { S.args_off = start; S.args_len = len; S.tc_dec = (S.tc_dec & ~0xC0u) | (d2 << 6); } break;
                 default: break;
                 }
             }
@@ -308,7 +317,7 @@ __device__ void v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, WarpSm
         }
         if (L.n_choices > 0) {
             ParseCtx cx; cx.sm = P.out; cx.P = &P; cx.S = nullptr; cx.emitted = true; cx.out_delta = 0;
-            Span ct = capture(cx, (int)L.content_off, (int)(L.content_off + L.content_len), (L.sf & SF_CDEC) != 0);
+            Span ct = capture(cx, (int)L.content_off, (int)(L.content_off + L.content_len), ((L.sf & SF_CDEC) ? 1 : 0) | ((L.sf & SF_CBAD) ? 2 : 0));
             r.content_off = ct.len ? ct.off : 0; r.content_len = ct.len;
             if (ct.text && ct.len) r.flags |= SSE_F_CONTENT_TEXT;
             r.flags |= L.finish << SSE_F_FINISH_SHIFT;
@@ -707,16 +716,28 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
             }
         }
         head += min(avail, n_idle);
-        // ------------------------------------------------------------------ automaton steps
+        // ------------------------------------------------------------------ automaton: rounds of K plain steps, then
+        // every lane that stopped at an action runs it (all lanes dispatch together: the divergent part is shared)
         #pragma unroll 1
-        for (int it = 0; it < STEPS; it++) {
-            if (L.busy) {
-                if (L.p >= L.pe) {
-                    v2_finish_line(P, L, S, W);
-                    SegSlot &sl = W.slots[L.slot];
-                    __threadfence_block();
-                    if (atomicSub(&sl.pending, 1) == 1) v2_finalize_segment(P, sl);
-                } else {
+        for (int round = 0; round < ROUNDS; round++) {
+            uint32_t pend = 0;                       // action | cls << 8 | in_str << 16 | in_tok << 17
+            #pragma unroll
+            for (int k = 0; k < KSTEPS; k++) {
+                if (L.p < L.pe && pend == 0) {
+                    if (L.st == S_VSTR && L.km == TRIE_DEAD) {
+                        // inside a long string value: jump to the next '"', '\\', control or non-ASCII byte of the window
+                        const uint32_t i = L.p & 15u;
+                        unsigned long long lo = ((unsigned long long)special_mask4(L.win.y) << 32) | special_mask4(L.win.x);
+                        unsigned long long hi = ((unsigned long long)special_mask4(L.win.w) << 32) | special_mask4(L.win.z);
+                        if (i < 8) lo &= ~0ull << (i * 8); else { lo = 0; hi &= ~0ull << ((i - 8) * 8); }
+                        uint32_t j = lo ? (uint32_t)(__ffsll((long long)lo) - 1) >> 3 : (hi ? 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3) : 16u);
+                        uint32_t n = min(j - i, L.pe - L.p);
+                        if (n) {
+                            L.p += n; L.slen += n;
+                            if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
+                            continue;
+                        }
+                    }
                     const uint32_t wsel = (L.p >> 2) & 3u;
                     const uint32_t w01 = (wsel & 1u) ? L.win.y : L.win.x, w23 = (wsel & 1u) ? L.win.w : L.win.z;
                     const uint32_t w = (wsel & 2u) ? w23 : w01;
@@ -725,21 +746,40 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
                     const uint32_t cls = e & 63u;
                     const bool in_str = (L.st - S_KSTR) < 12u || L.st >= S_V8_1;
                     const bool in_tok = in_str || (L.st - S_NMINUS) < 8u;
-                    const uint32_t kmn = in_str ? (uint32_t)T.kt[L.km * NSYM + ((e >> 8) & 31u)] : (uint32_t)TRIE_ROOT;
-                    uint32_t t = T.tr[L.st * NCLS + cls];
-                    for (;;) {
-                        if (t < A_FIRST) { L.st = t; break; }            // plain transition
-                        if (!v2_action(P, T, L, S, t)) break;            // the action chose the next state
-                        t = T.tr[L.st * NCLS + cls];                     // redo: same byte, new state
-                    }
-                    // per-string flags / token length / trie state for the next byte
-                    uint32_t nf = (cls == C_BSLASH ? SF_ESC : 0u) | (cls >= C_H80 ? SF_HI : 0u) | ((e & CLS_UPPER) ? SF_UPPER : 0u);
-                    L.sf = in_str ? (L.sf | nf) : (L.sf & ~SF_STRMASK);
-                    L.slen = in_tok ? L.slen + 1 : 0;
-                    L.km = kmn;
-                    L.p++;
-                    if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
+                    const uint32_t t = T.tr[L.st * NCLS + cls];
+                    if (t < A_FIRST) {
+                        L.km = in_str ? (uint32_t)T.kt[L.km * NSYM + ((e >> 8) & 31u)] : (uint32_t)TRIE_ROOT;
+                        const uint32_t nf = (cls == C_BSLASH ? SF_ESC : 0u) | (cls >= C_H80 ? SF_HI : 0u) | ((e & CLS_UPPER) ? SF_UPPER : 0u);
+                        L.sf = in_str ? (L.sf | nf) : (L.sf & ~SF_STRMASK);
+                        L.slen = in_tok ? L.slen + 1 : 0;
+                        L.st = t;
+                        L.p++;
+                        if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
+                    } else pend = t | (cls << 8) | (in_str ? 0x10000u : 0u) | (in_tok ? 0x20000u : 0u);
                 }
+            }
+            if (pend) {
+                uint32_t t = pend & 0xFFu;
+                const uint32_t cls = (pend >> 8) & 0xFFu;
+                for (;;) {
+                    if (!v2_action(P, T, L, S, t)) break;            // the action chose the next state
+                    t = T.tr[L.st * NCLS + cls];                     // redo: same byte, new state
+                    if (t < A_FIRST) { L.st = t; break; }
+                }
+                const bool in_str = (pend & 0x10000u) != 0;
+                L.km = in_str ? (uint32_t)TRIE_DEAD : (uint32_t)TRIE_ROOT;
+                const uint32_t nf = (cls == C_BSLASH ? SF_ESC : 0u) | (cls >= C_H80 ? SF_HI : 0u);
+                L.sf = in_str ? (L.sf | nf) : (L.sf & ~SF_STRMASK);
+                L.slen = (pend & 0x20000u) ? L.slen + 1 : 0;
+                L.p++;
+                if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
+            }
+            if (L.busy && L.p >= L.pe) {
+                v2_finish_line(P, L, S, W);
+                SegSlot &sl = W.slots[L.slot];
+                __threadfence_block();
+                if (atomicSub(&sl.pending, 1) == 1) v2_finalize_segment(P, sl);
+                L.p = L.pe = 0;
             }
         }
     }
