@@ -322,6 +322,57 @@ __device__ __noinline__ uint32_t json_unquote(const uint8_t *sm, int s, int e, u
     if (i < e) return cap + 1;   // did not fit
     return n;
 }
+// Single-pass unquote into a 4-byte aligned destination (text arena): same semantics as json_unquote, tight loop,
+// bytes gathered into 32-bit stores. Returns the decoded length.
+__device__ __noinline__ uint32_t json_unquote_write(const uint8_t *__restrict__ src, int s, int e, uint8_t *__restrict__ dst) {
+    uint32_t n = 0, acc = 0;
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+    int i = s;
+    auto put = [&](uint32_t c) {
+        acc |= c << ((n & 3u) * 8u);
+        if ((n & 3u) == 3u) { d32[n >> 2] = acc; acc = 0; }
+        n++;
+    };
+    while (i < e) {
+        uint32_t c = src[i];
+        if (c != '\\' && c < 0x80) { put(c); i++; continue; }
+        if (c == '\\') {
+            uint32_t esc = src[i + 1];
+            i += 2;
+            uint32_t r;
+            switch (esc) {
+            case 'b': r = 8; break;
+            case 'f': r = 12; break;
+            case 'n': r = 10; break;
+            case 'r': r = 13; break;
+            case 't': r = 9; break;
+            case 'u': {
+                r = (uint32_t)hex4(src + i);
+                i += 4;
+                if (r >= 0xD800 && r < 0xE000) {
+                    int r1 = -1;
+                    if (i + 6 <= e && src[i] == '\\' && src[i + 1] == 'u') r1 = hex4(src + i + 2);
+                    if (r < 0xDC00 && r1 >= 0xDC00 && r1 < 0xE000) { r = 0x10000 + ((r - 0xD800) << 10) + ((uint32_t)r1 - 0xDC00); i += 6; }
+                    else r = 0xFFFD;
+                }
+                break;
+            }
+            default: r = esc; break;
+            }
+            if (r < 0x80) put(r);
+            else if (r < 0x800) { put(0xC0 | (r >> 6)); put(0x80 | (r & 0x3F)); }
+            else if (r < 0x10000) { put(0xE0 | (r >> 12)); put(0x80 | ((r >> 6) & 0x3F)); put(0x80 | (r & 0x3F)); }
+            else { put(0xF0 | (r >> 18)); put(0x80 | ((r >> 12) & 0x3F)); put(0x80 | ((r >> 6) & 0x3F)); put(0x80 | (r & 0x3F)); }
+        } else {
+            int k = utf8_valid_len(src + i, e - i);
+            if (k == 0) { put(0xEF); put(0xBF); put(0xBD); i++; }
+            else { for (int q = 0; q < k; q++) put(src[i + q]); i += k; }
+        }
+    }
+    if (n & 3u) d32[n >> 2] = acc;     // the allocation is padded to a multiple of 4
+    return n;
+}
+
 // encoding/json foldName equality (Go >= 1.21): ASCII case-insensitive, U+212A == 'k', U+017F == 's'
 __device__ __noinline__ bool key_eq(const uint8_t *k, int n, const char *name, int m, bool fold) {
     if (!fold) {
@@ -376,11 +427,11 @@ __device__ __noinline__ Span capture(const ParseCtx &cx, int s, int e, int dec) 
     const uint32_t raw = (uint32_t)(e - s);
     r.text = true; r.len = 0; r.off = 0;
     if (raw == 0) return r;
-    const uint32_t bound = (dec & 2) ? 3u * raw : raw;
+    const uint32_t bound = (((dec & 2) ? 3u * raw : raw) + 3u) & ~3u;   // 4-byte aligned allocations
     uint32_t o = atomicAdd(&cx.P->ctr->text_bytes, bound);
     if (o + bound > cx.P->cap_text) { atomicExch(&cx.P->ctr->status, (int)SSE_ERR_OVERFLOW); return r; }
     r.off = o;
-    if (dec) r.len = json_unquote(cx.sm, s, e, cx.P->text + o, 0x7FFFFFF0u);
+    if (dec) r.len = json_unquote_write(cx.sm, s, e, cx.P->text + o);
     else { for (int i = s; i < e; i++) cx.P->text[o + (i - s)] = cx.sm[i]; r.len = raw; }
     return r;
 }
@@ -657,6 +708,30 @@ __device__ void copy_s2g_bytes(uint8_t *g_dst, const uint8_t *sm_src, int n) {
 }
 __device__ void copy_g2g_bytes(uint8_t *g_dst, const uint8_t *g_src, int n) {
     for (int i = lane_id(); i < n; i += 32) g_dst[i] = g_src[i];
+}
+
+// Warp-cooperative copy of n bytes shared -> global with arbitrary alignment on both sides: the destination is written
+// as aligned 16-byte vectors, the source is read as aligned words and funnel-shifted into place.
+__device__ __forceinline__ void copy_s2g_vec(uint8_t *__restrict__ g_dst, const uint8_t *__restrict__ sm_src, int n) {
+    const int lane = (int)lane_id();
+    if (n < 48) { for (int i = lane; i < n; i += 32) g_dst[i] = sm_src[i]; return; }
+    const int head = (int)((16u - ((uint32_t)(uintptr_t)g_dst & 15u)) & 15u);
+    if (lane < head) g_dst[lane] = sm_src[lane];
+    const int nch = (n - head) >> 4;
+    const uint8_t *sb = sm_src + head;
+    const uint32_t sh = ((uint32_t)(uintptr_t)sb & 3u) * 8u;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>((uintptr_t)sb & ~(uintptr_t)3);
+    uint4 *gd = reinterpret_cast<uint4 *>(g_dst + head);
+    for (int c = lane; c < nch; c += 32) {
+        const uint32_t *w = sw + c * 4;
+        uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4];
+        uint4 v;
+        v.x = __funnelshift_r(a0, a1, sh); v.y = __funnelshift_r(a1, a2, sh);
+        v.z = __funnelshift_r(a2, a3, sh); v.w = __funnelshift_r(a3, a4, sh);
+        gd[c] = v;
+    }
+    const int done = head + (nch << 4);
+    if (lane < n - done) g_dst[done + lane] = sm_src[done + lane];
 }
 
 struct RunChain {           // lane-uniform bookkeeping of a segment's result runs

@@ -402,7 +402,10 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
         // ------------------------------------------------------------------ produce when lanes would starve
         const unsigned idle_mask = __ballot_sync(FULL, !L.busy);
         const uint32_t n_idle = __popc(idle_mask), avail = tail - head;
-        bool want = (avail < n_idle) && (pr.phase != 0 || pr.more) && (RING - avail >= (uint32_t)LT_MAX);
+        // lanes start new lines together (batch-synchronous refill): lines of one stream share their structure, so lanes
+        // that start together stay in lockstep and share the divergent action code
+        const bool all_idle = n_idle == 32;
+        bool want = all_idle && (avail < 32u) && (pr.phase != 0 || pr.more) && (RING - avail >= (uint32_t)LT_MAX);
         if (want && pr.phase == 0) {
             // a free segment slot?
             int fs = -1;
@@ -626,11 +629,10 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
                                 uint8_t *dst = P.out + o;
                                 const uint8_t *sp = buf + e.src_s;
                                 if (mode & SSE_MODE_R) {
-                                    int body = (int)e.flen - 2;
-                                    for (int k = lane; k < (int)e.flen; k += 32) dst[k] = (k < body) ? sp[k] : (uint8_t)'\n';
-                                } else {
-                                    for (int k = lane; k < (int)e.flen; k += 32) dst[k] = sp[k];
-                                }
+                                    const int body = (int)e.flen - 2;     // "data: " + payload, contiguous in the window
+                                    copy_s2g_vec(dst, sp, body);
+                                    if (lane < 2) dst[body + lane] = (uint8_t)'\n';
+                                } else copy_s2g_vec(dst, sp, (int)e.flen);
                                 o += e.flen;
                             }
                         }
@@ -700,8 +702,8 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
             continue;
         }
         // ------------------------------------------------------------------ idle lanes take work items
-        if (!L.busy) {
-            const uint32_t rank = __popc(idle_mask & ((1u << lane) - 1u));
+        if (all_idle) {
+            const uint32_t rank = lane;
             if (rank < avail) {
                 const uint4 it = W.ring[(head + rank) & (RING - 1)];
                 L.p = it.x; L.pe = it.x + it.y; L.rec = it.z; L.frame = it.w & 0x1FFFFFFFu;
@@ -715,7 +717,7 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
                 if (L.p < L.pe) L.win = ldcg16(P.out, L.p);
             }
         }
-        head += min(avail, n_idle);
+        if (all_idle) head += min(avail, 32u);
         // ------------------------------------------------------------------ automaton: rounds of K plain steps, then
         // every lane that stopped at an action runs it (all lanes dispatch together: the divergent part is shared)
         #pragma unroll 1
