@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+N_SLOTS = 3      # batches in flight on the end-to-end path: H2D, kernel and D2H of consecutive batches overlap
 METRIC = "SSE chunks/sec @ 64k concurrent streams"
 UNIT = "chunks/s"
 
@@ -163,6 +164,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=65536, help="concurrent streams per GPU")
     ap.add_argument("--workload", default="C4")
+    ap.add_argument("--mode", type=int, default=None, help="override the workload's mode bits (0 P, 2 P+parse, 3 R+parse)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -184,8 +186,10 @@ def main():
 
     from inference_gateway_b200 import SseEngine, shard as sh
     bodies, mode, n_events = build_workload(args.streams, rank, args.workload)
+    if args.mode is not None:
+        mode = args.mode
     in_payload = sum(map(len, bodies))
-    eng = SseEngine(device=local_rank, max_conns=len(bodies), bytes_per_batch=in_payload, n_slots=2, carry_slot_bytes=16384)
+    eng = SseEngine(device=local_rank, max_conns=len(bodies), bytes_per_batch=in_payload, n_slots=N_SLOTS, carry_slot_bytes=16384)
     # a non-default torch stream: its handle is passed to the library so that the kernels, the resets and the
     # CUDA events of the timed region all live on the same stream (handle 0 would mean "library stream")
     tstream = torch.cuda.Stream()
@@ -209,6 +213,9 @@ def main():
     counts = dict(frames=int(res.raw.n_frames), recs=int(res.raw.n_recs), tcs=int(res.raw.n_tcs), usages=int(res.raw.n_usages),
                   out_bytes=int(res.raw.out_bytes), text_bytes=int(res.raw.text_bytes), runs=int(res.raw.n_runs),
                   in_bytes=in_payload, segs=n_segs, events=n_events)
+    valid_frames = int(res.segs["frame_count"].astype(np.int64).sum()) + sum(
+        int(res.runs["frame_count"][j]) for j in range(int(res.raw.n_runs)))
+    counts["frames"] = valid_frames        # frames of lines after a terminating chunk are allocated but cut from the result
     terminated = int(np.count_nonzero(res.segs["flags"] & 1))
     ok_recs = int(np.count_nonzero(res.recs["flags"] & 1))
 
@@ -234,7 +241,7 @@ def main():
     if not args.no_e2e:
         eng.release(slot)
         slots = []
-        for _ in range(2):
+        for _ in range(N_SLOTS):
             s2, a2, g2 = eng.acquire()
             fill_slot(eng, a2, g2, bodies, mode)
             slots.append(s2)
@@ -252,7 +259,7 @@ def main():
                 eng.reset_all(0)
                 eng.submit(s2, n_segs, in_bytes)
                 inflight.append(s2)
-                if len(inflight) == 2:
+                if len(inflight) == N_SLOTS:
                     s_old = inflight.pop(0)
                     r = eng.collect(s_old)
                     frames += int(r.raw.n_frames)
@@ -263,7 +270,7 @@ def main():
                 eng.release(s_old)
             return frames
 
-        e2e_steps(2)
+        e2e_steps(N_SLOTS)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -276,7 +283,7 @@ def main():
         fr_all = sh.reduce_counters({"f": fr}, world)["f"]
         e2e = {"value": fr_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": k_e2e, "ms_per_step": 1e3 * e2e_s / k_e2e,
-               "path": "sse_acquire/sse_submit/sse_collect/sse_release, 2 slots in flight, host buffers pinned"}
+               "path": f"sse_acquire/sse_submit/sse_collect/sse_release, {N_SLOTS} slots in flight, host buffers pinned"}
 
     dev_ms = sh.max_over_ranks(dev_ms, world)
     tot = sh.reduce_counters(counts, world)

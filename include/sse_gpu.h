@@ -67,7 +67,8 @@ typedef struct {
     uint32_t flags;            /* SSE_FLAG_* */
 } sse_config;
 
-#define SSE_FLAG_KERNEL_V1 1u  /* use the first-generation kernel (sequential per-lane decoder); default is v2 */
+#define SSE_FLAG_KERNEL_V1 1u  /* fused first-generation kernel (sequential per-lane decoder) */
+#define SSE_FLAG_KERNEL_V2 2u  /* fused producer/consumer kernel (table-driven automaton); default is the split pipeline */
 
 /* One segment = the bytes read from ONE connection since the previous batch. in_off is 16-byte aligned. */
 typedef struct {

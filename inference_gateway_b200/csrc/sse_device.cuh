@@ -30,7 +30,9 @@ struct Counters {
     uint32_t text_bytes;
     uint32_t n_runs;
     int32_t  status;
-    uint32_t pad[7];
+    uint32_t n_items;      // split pipeline: work items written by the produce kernel
+    uint32_t item_ticket;  // split pipeline: next item batch for the decode kernel
+    uint32_t pad[5];
 };
 
 struct KParams {
@@ -51,9 +53,14 @@ struct KParams {
     sse_run *runs;           uint32_t cap_runs;
     sse_seg_result *seg_results;
     Counters *ctr;
+    // split pipeline (produce -> decode -> finalize)
+    uint4 *items;            uint32_t cap_items;   // src, len | rmode << 31, rec, seg
+    uint32_t *seg_term;                            // per segment: smallest terminating record index, SSE_NONE if none
 };
 
 // launch wrappers (sse_kernel.cu)
 int sse_launch_stream_kernel(const KParams &p, void *stream, int sm_count);            // v1: per-lane sequential decoder
+int sse_launch_produce_kernel(const KParams &p, void *stream, int sm_count);           // split pipeline, stage 1
+int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int device);  // split pipeline, stages 2+3
 int sse_v2_prepare(int device);                                                        // builds + uploads the automaton tables
 int sse_launch_stream_kernel_v2(const KParams &p, void *stream, int sm_count, int device);

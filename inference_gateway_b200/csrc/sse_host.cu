@@ -41,6 +41,7 @@ struct Slot {
     uint8_t *d_out = nullptr; sse_frame *d_frames = nullptr; sse_rec *d_recs = nullptr; sse_tc *d_tcs = nullptr;
     sse_usage *d_usages = nullptr; uint8_t *d_text = nullptr; sse_run *d_runs = nullptr; sse_seg_result *d_segres = nullptr;
     Counters *d_ctr = nullptr;
+    uint4 *d_items = nullptr; uint32_t *d_segterm = nullptr;   // split pipeline scratch (device only)
     uint32_t n_segs = 0, in_bytes = 0;
 };
 
@@ -71,7 +72,7 @@ void free_slot(Slot &s) {
     cudaFreeHost(s.h_tcs); cudaFreeHost(s.h_usages); cudaFreeHost(s.h_text); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_segres);
     cudaFreeHost(s.h_ctr);
     cudaFree(s.d_in); cudaFree(s.d_segs); cudaFree(s.d_out); cudaFree(s.d_frames); cudaFree(s.d_recs); cudaFree(s.d_tcs);
-    cudaFree(s.d_usages); cudaFree(s.d_text); cudaFree(s.d_runs); cudaFree(s.d_segres); cudaFree(s.d_ctr);
+    cudaFree(s.d_usages); cudaFree(s.d_text); cudaFree(s.d_runs); cudaFree(s.d_segres); cudaFree(s.d_ctr); cudaFree(s.d_items); cudaFree(s.d_segterm);
 }
 
 KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
@@ -86,6 +87,7 @@ KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
     p.text = s.d_text; p.cap_text = c->cfg.text_arena_bytes;
     p.runs = s.d_runs; p.cap_runs = c->cfg.max_runs;
     p.seg_results = s.d_segres; p.ctr = s.d_ctr;
+    p.items = s.d_items; p.cap_items = c->cfg.max_recs; p.seg_term = s.d_segterm;
     return p;
 }
 
@@ -110,10 +112,15 @@ int do_launch(sse_ctx *c, Slot &s, uint32_t n_segs, cudaStream_t st) {
     CU(cudaMemsetAsync(s.d_ctr, 0, sizeof(Counters), st));
     if (n_segs) {
         KParams p = make_params(c, s, n_segs);
-        int e = (c->cfg.flags & SSE_FLAG_KERNEL_V1) ? sse_launch_stream_kernel(p, (void *)st, c->sm_count)
-                                                    : sse_launch_stream_kernel_v2(p, (void *)st, c->sm_count, c->device);
-        if (e != 0) { cu_ok((cudaError_t)e, "sse_stream_kernel launch"); return SSE_ERR_CUDA; }
-        c->launches++;
+        int e;
+        if (c->cfg.flags & SSE_FLAG_KERNEL_V1) { e = sse_launch_stream_kernel(p, (void *)st, c->sm_count); c->launches += 1; }
+        else if (c->cfg.flags & SSE_FLAG_KERNEL_V2) { e = sse_launch_stream_kernel_v2(p, (void *)st, c->sm_count, c->device); c->launches += 1; }
+        else {   // default: split pipeline produce -> decode -> finalize
+            e = sse_launch_produce_kernel(p, (void *)st, c->sm_count);
+            if (e == 0) e = sse_launch_decode_finalize(p, (void *)st, c->sm_count, c->device);
+            c->launches += 3;
+        }
+        if (e != 0) { cu_ok((cudaError_t)e, "stream kernel launch"); return SSE_ERR_CUDA; }
     }
     s.n_segs = n_segs;
     return SSE_OK;
@@ -225,6 +232,7 @@ int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
         ok = ok && dalloc(s.d_out, cfg->out_arena_bytes) && dalloc(s.d_frames, cfg->max_frames) && dalloc(s.d_recs, cfg->max_recs);
         ok = ok && dalloc(s.d_tcs, cfg->max_tcs) && dalloc(s.d_usages, cfg->max_usages) && dalloc(s.d_text, cfg->text_arena_bytes);
         ok = ok && dalloc(s.d_runs, cfg->max_runs) && dalloc(s.d_segres, cfg->max_segs) && dalloc(s.d_ctr, 1);
+        ok = ok && dalloc(s.d_items, cfg->max_recs) && dalloc(s.d_segterm, cfg->max_segs);
     }
     if (!ok) { sse_destroy(c); return SSE_ERR_CUDA; }
     *out = c;

@@ -17,6 +17,9 @@
 namespace {
 
 // ---------------------------------------------------------------- the kernel
+// SPLIT = false: the complete v1 kernel. SPLIT = true: stage 1 of the split pipeline (stage, split, classify, emit;
+// one work item per emitted data line goes to P.items for sse_decode_kernel; no early termination here).
+template <bool SPLIT>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 sse_stream_kernel(const KParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -46,6 +49,7 @@ sse_stream_kernel(const KParams P) {
         RunChain rc; rc.have_first = false; rc.last_idx = SSE_NONE;
         rc.first.frame_first = rc.first.frame_count = rc.first.rec_first = rc.first.rec_count = 0; rc.first.next = SSE_NONE;
         uint32_t seg_flags = 0;
+        if (SPLIT && lane == 0) P.seg_term[s] = SSE_NONE;
 
         if (cst.flags & (CONN_FINISHED | CONN_DEAD)) {
             if (lane == 0) {
@@ -202,14 +206,27 @@ sse_stream_kernel(const KParams P) {
                     pre_b[h] = tot_b + sb - vb; pre_f[h] = tot_f + sf - vf; pre_r[h] = tot_r + sr - vr;
                     tot_b += __shfl_sync(FULL, sb, 31); tot_f += __shfl_sync(FULL, sf, 31); tot_r += __shfl_sync(FULL, sr, 31);
                 }
+                uint32_t my_q = 0;
+                if (SPLIT) {
+                    #pragma unroll
+                    for (int h = 0; h < 2; h++) my_q += (my_parse[h] && my_kind[h] == K_EMIT) ? 1u : 0u;
+                }
+                uint32_t pre_q = my_q, tot_q = 0, qb = 0;
+                if (SPLIT) {
+                    #pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, pre_q, d); if ((int)lane >= d) pre_q += t; }
+                    tot_q = __shfl_sync(FULL, pre_q, 31);
+                    pre_q -= my_q;
+                }
                 uint32_t ob = 0, fb = 0, rb = 0;
                 if (lane == 0) {
-                    if (tot_b) ob = atomicAdd(&P.ctr->out_bytes, tot_b);
+                    if (SPLIT && tot_q) qb = atomicAdd(&P.ctr->n_items, tot_q);
+                    if (tot_b) ob = atomicAdd(&P.ctr->out_bytes, (tot_b + 15u) & ~15u);
                     if (tot_f) fb = atomicAdd(&P.ctr->n_frames, tot_f);
                     if (tot_r) rb = atomicAdd(&P.ctr->n_recs, tot_r);
                 }
-                ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0);
-                if (ob + tot_b > P.cap_out || fb + tot_f > P.cap_frames || rb + tot_r > P.cap_recs) {
+                ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0); qb = __shfl_sync(FULL, qb, 0);
+                if (ob + tot_b + 16 > P.cap_out || fb + tot_f > P.cap_frames || rb + tot_r > P.cap_recs || (SPLIT && qb + tot_q > P.cap_items)) {
                     if (lane == 0) atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW);
                     overflow = true; break;
                 }
@@ -227,11 +244,10 @@ sse_stream_kernel(const KParams P) {
                         uint8_t *dst = P.out + o;
                         const uint8_t *sp = buf + e.src_s;
                         if (mode & SSE_MODE_R) {
-                            int body = (int)e.flen - 2;            // "data: " + payload is contiguous in the window
-                            for (int k = lane; k < (int)e.flen; k += 32) dst[k] = (k < body) ? sp[k] : (uint8_t)'\n';
-                        } else {
-                            for (int k = lane; k < (int)e.flen; k += 32) dst[k] = sp[k];
-                        }
+                            const int body = (int)e.flen - 2;      // "data: " + payload is contiguous in the window
+                            copy_s2g_vec(dst, sp, body);
+                            if (lane < 2) dst[body + lane] = (uint8_t)'\n';
+                        } else copy_s2g_vec(dst, sp, (int)e.flen);
                         o += e.flen;
                     }
                 }
@@ -245,6 +261,20 @@ sse_stream_kernel(const KParams P) {
                         ParseCtx cx; cx.sm = buf; cx.P = &P; cx.S = &cs.schema;
                         cx.emitted = my_kind[h] == K_EMIT;
                         cx.out_delta = (int64_t)(ob + pre_b[h]) - (int64_t)e.src_s;
+                        if (SPLIT && my_kind[h] == K_EMIT) {
+                            // lane order within the round: items of lane L (h = 0 then h = 1) follow those of lanes < L
+                            const uint32_t qi = qb + pre_q + ((h == 1 && my_parse[0] && my_kind[0] == K_EMIT) ? 1u : 0u);
+                            sse_rec stub;
+                            stub.frame = fb + pre_f[h]; stub.flags = 0; stub.content_off = stub.content_len = 0; stub.tc_first = SSE_NONE;
+                            stub.tc_count = 0; stub.n_choices = 0; stub.usage = SSE_NONE; stub.payload_len = (uint32_t)(e.pay_e - e.pay_s);
+                            P.recs[rb + pre_r[h]] = stub;
+                            uint4 it;
+                            it.x = ob + pre_b[h] + (uint32_t)(e.pay_s - e.src_s);
+                            it.y = (uint32_t)(e.pay_e - e.pay_s) | ((mode & SSE_MODE_R) ? 0x80000000u : 0u);
+                            it.z = rb + pre_r[h]; it.w = s;
+                            P.items[qi] = it;
+                            continue;
+                        }
                         ParseOut po;
                         if (my_kind[h] == K_DONE_EXACT) { po.flags = 0; po.content_off = po.content_len = 0; po.tc_first = SSE_NONE; po.tc_count = po.n_choices = 0; po.usage = SSE_NONE; }
                         else decode_chunk(cx, e.pay_s, e.pay_e, po);
@@ -341,24 +371,26 @@ sse_stream_kernel(const KParams P) {
 
 } // namespace
 
-int sse_launch_stream_kernel(const KParams &p, void *stream, int sm_count) {
+template <bool SPLIT>
+static int launch_v1(const KParams &p, void *stream, int sm_count) {
     static bool attr_set = false;
+    static int ctas_per_sm = 0;
     const size_t smem = sizeof(CtaSmem);
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(sse_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(sse_stream_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
         int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sse_stream_kernel, WARPS_PER_CTA * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sse_stream_kernel<SPLIT>, WARPS_PER_CTA * 32, smem);
         if (e != cudaSuccess) return (int)e;
         ctas_per_sm = n > 0 ? n : 1;
+        attr_set = true;
     }
     int grid = sm_count * ctas_per_sm;   // persistent: one resident wave, warps pull segments by ticket
     int need = (int)((p.n_segs + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
     if (need < grid) grid = need > 0 ? need : 1;
-    sse_stream_kernel<<<grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(p);
+    sse_stream_kernel<SPLIT><<<grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
+
+int sse_launch_stream_kernel(const KParams &p, void *stream, int sm_count) { return launch_v1<false>(p, stream, sm_count); }
+int sse_launch_produce_kernel(const KParams &p, void *stream, int sm_count) { return launch_v1<true>(p, stream, sm_count); }

@@ -293,7 +293,8 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
 }
 
 // A line retires: final syntax check, record, termination bookkeeping (agent.go:205-242).
-__device__ void v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, WarpSmem2 &W) {
+__device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S) {
+    bool terminates = false;
     if (!(L.sf & SF_SYN)) {
         if (L.depth == 0 && (L.st == S_NZERO || L.st == S_NINT || L.st == S_NFRAC || L.st == S_NEXP)) {
             v2_number_end(P, L, S, L.pe);
@@ -327,13 +328,14 @@ __device__ void v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, WarpSm
             r.tc_count = (uint16_t)min(L.tc_count, 0xFFFFu);
             if ((L.sf & SF_RMODE) && (L.finish == SSE_FIN_STOP || L.finish == SSE_FIN_TOOL_CALLS)) {
                 r.flags |= SSE_F_TERMINATES;
-                atomicMin(&W.slots[L.slot].term, ((unsigned long long)L.rec << 32) | L.frame);
+                terminates = true;
             }
         }
     }
     r.payload_len = L.plen;
     P.recs[L.rec] = r;
     L.busy = false;
+    return terminates;
 }
 
 // Called by whichever lane (or the producer) drops a segment's pending count to zero.
@@ -360,6 +362,64 @@ __device__ void v2_finalize_segment(const KParams &P, SegSlot &sl) {
     }
     __threadfence_block();
     sl.used = 0;
+}
+
+// One round of the per-lane automaton: KSTEPS plain steps, then the pending action (if any) of every lane.
+__device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S) {
+    uint32_t pend = 0;                       // action | cls << 8 | in_str << 16 | in_tok << 17
+    #pragma unroll
+    for (int k = 0; k < KSTEPS; k++) {
+        if (L.p < L.pe && pend == 0) {
+            if (L.st == S_VSTR && L.km == TRIE_DEAD) {
+                // inside a long string value: jump to the next '"', '\\', control or non-ASCII byte of the window
+                const uint32_t i = L.p & 15u;
+                unsigned long long lo = ((unsigned long long)special_mask4(L.win.y) << 32) | special_mask4(L.win.x);
+                unsigned long long hi = ((unsigned long long)special_mask4(L.win.w) << 32) | special_mask4(L.win.z);
+                if (i < 8) lo &= ~0ull << (i * 8); else { lo = 0; hi &= ~0ull << ((i - 8) * 8); }
+                uint32_t j = lo ? (uint32_t)(__ffsll((long long)lo) - 1) >> 3 : (hi ? 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3) : 16u);
+                uint32_t n = min(j - i, L.pe - L.p);
+                if (n) {
+                    L.p += n; L.slen += n;
+                    if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
+                    continue;
+                }
+            }
+            const uint32_t wsel = (L.p >> 2) & 3u;
+            const uint32_t w01 = (wsel & 1u) ? L.win.y : L.win.x, w23 = (wsel & 1u) ? L.win.w : L.win.z;
+            const uint32_t w = (wsel & 2u) ? w23 : w01;
+            const uint32_t c = (w >> ((L.p & 3u) * 8u)) & 0xFFu;
+            const uint32_t e = T.clssym[c];
+            const uint32_t cls = e & 63u;
+            const bool in_str = (L.st - S_KSTR) < 12u || L.st >= S_V8_1;
+            const bool in_tok = in_str || (L.st - S_NMINUS) < 8u;
+            const uint32_t t = T.tr[L.st * NCLS + cls];
+            if (t < A_FIRST) {
+                L.km = in_str ? (uint32_t)T.kt[L.km * NSYM + ((e >> 8) & 31u)] : (uint32_t)TRIE_ROOT;
+                const uint32_t nf = (cls == C_BSLASH ? SF_ESC : 0u) | (cls >= C_H80 ? SF_HI : 0u) | ((e & CLS_UPPER) ? SF_UPPER : 0u);
+                L.sf = in_str ? (L.sf | nf) : (L.sf & ~SF_STRMASK);
+                L.slen = in_tok ? L.slen + 1 : 0;
+                L.st = t;
+                L.p++;
+                if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
+            } else pend = t | (cls << 8) | (in_str ? 0x10000u : 0u) | (in_tok ? 0x20000u : 0u);
+        }
+    }
+    if (pend) {
+        uint32_t t = pend & 0xFFu;
+        const uint32_t cls = (pend >> 8) & 0xFFu;
+        for (;;) {
+            if (!v2_action(P, T, L, S, t)) break;            // the action chose the next state
+            t = T.tr[L.st * NCLS + cls];                     // redo: same byte, new state
+            if (t < A_FIRST) { L.st = t; break; }
+        }
+        const bool in_str = (pend & 0x10000u) != 0;
+        L.km = in_str ? (uint32_t)TRIE_DEAD : (uint32_t)TRIE_ROOT;
+        const uint32_t nf = (cls == C_BSLASH ? SF_ESC : 0u) | (cls >= C_H80 ? SF_HI : 0u);
+        L.sf = in_str ? (L.sf | nf) : (L.sf & ~SF_STRMASK);
+        L.slen = (pend & 0x20000u) ? L.slen + 1 : 0;
+        L.p++;
+        if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
+    }
 }
 
 struct Producer {                  // warp-uniform coroutine state of the segment being produced
@@ -722,69 +782,107 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
         // every lane that stopped at an action runs it (all lanes dispatch together: the divergent part is shared)
         #pragma unroll 1
         for (int round = 0; round < ROUNDS; round++) {
-            uint32_t pend = 0;                       // action | cls << 8 | in_str << 16 | in_tok << 17
-            #pragma unroll
-            for (int k = 0; k < KSTEPS; k++) {
-                if (L.p < L.pe && pend == 0) {
-                    if (L.st == S_VSTR && L.km == TRIE_DEAD) {
-                        // inside a long string value: jump to the next '"', '\\', control or non-ASCII byte of the window
-                        const uint32_t i = L.p & 15u;
-                        unsigned long long lo = ((unsigned long long)special_mask4(L.win.y) << 32) | special_mask4(L.win.x);
-                        unsigned long long hi = ((unsigned long long)special_mask4(L.win.w) << 32) | special_mask4(L.win.z);
-                        if (i < 8) lo &= ~0ull << (i * 8); else { lo = 0; hi &= ~0ull << ((i - 8) * 8); }
-                        uint32_t j = lo ? (uint32_t)(__ffsll((long long)lo) - 1) >> 3 : (hi ? 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3) : 16u);
-                        uint32_t n = min(j - i, L.pe - L.p);
-                        if (n) {
-                            L.p += n; L.slen += n;
-                            if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
-                            continue;
-                        }
-                    }
-                    const uint32_t wsel = (L.p >> 2) & 3u;
-                    const uint32_t w01 = (wsel & 1u) ? L.win.y : L.win.x, w23 = (wsel & 1u) ? L.win.w : L.win.z;
-                    const uint32_t w = (wsel & 2u) ? w23 : w01;
-                    const uint32_t c = (w >> ((L.p & 3u) * 8u)) & 0xFFu;
-                    const uint32_t e = T.clssym[c];
-                    const uint32_t cls = e & 63u;
-                    const bool in_str = (L.st - S_KSTR) < 12u || L.st >= S_V8_1;
-                    const bool in_tok = in_str || (L.st - S_NMINUS) < 8u;
-                    const uint32_t t = T.tr[L.st * NCLS + cls];
-                    if (t < A_FIRST) {
-                        L.km = in_str ? (uint32_t)T.kt[L.km * NSYM + ((e >> 8) & 31u)] : (uint32_t)TRIE_ROOT;
-                        const uint32_t nf = (cls == C_BSLASH ? SF_ESC : 0u) | (cls >= C_H80 ? SF_HI : 0u) | ((e & CLS_UPPER) ? SF_UPPER : 0u);
-                        L.sf = in_str ? (L.sf | nf) : (L.sf & ~SF_STRMASK);
-                        L.slen = in_tok ? L.slen + 1 : 0;
-                        L.st = t;
-                        L.p++;
-                        if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
-                    } else pend = t | (cls << 8) | (in_str ? 0x10000u : 0u) | (in_tok ? 0x20000u : 0u);
-                }
-            }
-            if (pend) {
-                uint32_t t = pend & 0xFFu;
-                const uint32_t cls = (pend >> 8) & 0xFFu;
-                for (;;) {
-                    if (!v2_action(P, T, L, S, t)) break;            // the action chose the next state
-                    t = T.tr[L.st * NCLS + cls];                     // redo: same byte, new state
-                    if (t < A_FIRST) { L.st = t; break; }
-                }
-                const bool in_str = (pend & 0x10000u) != 0;
-                L.km = in_str ? (uint32_t)TRIE_DEAD : (uint32_t)TRIE_ROOT;
-                const uint32_t nf = (cls == C_BSLASH ? SF_ESC : 0u) | (cls >= C_H80 ? SF_HI : 0u);
-                L.sf = in_str ? (L.sf | nf) : (L.sf & ~SF_STRMASK);
-                L.slen = (pend & 0x20000u) ? L.slen + 1 : 0;
-                L.p++;
-                if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
-            }
+            v2_round(P, T, L, S);
             if (L.busy && L.p >= L.pe) {
-                v2_finish_line(P, L, S, W);
                 SegSlot &sl = W.slots[L.slot];
+                if (v2_finish_line(P, L, S)) atomicMin(&sl.term, ((unsigned long long)L.rec << 32) | L.frame);
                 __threadfence_block();
                 if (atomicSub(&sl.pending, 1) == 1) v2_finalize_segment(P, sl);
                 L.p = L.pe = 0;
             }
         }
     }
+}
+
+
+// ---------------------------------------------------------------- split pipeline, stage 2: decode
+// Persistent warps pull 32 work items at a time (lines of the same stream are adjacent, so the lanes of a batch walk
+// near-identical structure in lockstep); no producer code and no line window in this kernel: small instruction
+// footprint, shared memory only for the tables and the cold per-lane state.
+constexpr int V3_WARPS = 24;
+
+struct CtaSmem3 {
+    DfaTables T;
+    LaneScratch ls[V3_WARPS * 32];
+};
+
+__global__ void __launch_bounds__(V3_WARPS * 32, 1)
+sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    CtaSmem3 &cs = *reinterpret_cast<CtaSmem3 *>(smem_raw);
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(gT);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&cs.T);
+        for (int i = threadIdx.x; i < (int)(sizeof(DfaTables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const DfaTables &T = cs.T;
+    LaneScratch &S = cs.ls[threadIdx.x];
+    const uint32_t lane = lane_id();
+    const uint32_t n_items = min(P.ctr->n_items, P.cap_items);
+
+    Lane L; L.busy = false; L.p = L.pe = 0; L.win = make_uint4(0, 0, 0, 0);
+    L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.km = TRIE_ROOT; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
+    L.finish = 0; L.ct = L.ct1 = L.sstk = 0; L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
+    L.rec = L.frame = L.slot = L.plen = 0;
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&P.ctr->item_ticket, 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n_items) break;
+        const uint32_t idx = base + lane;
+        if (idx < n_items) {
+            const uint4 it = P.items[idx];
+            L.p = it.x; L.plen = it.y & 0x7FFFFFFFu; L.pe = it.x + L.plen; L.rec = it.z; L.slot = it.w;   // slot: segment index
+            L.frame = P.recs[it.z].frame;
+            L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.km = TRIE_ROOT; L.slen = 0;
+            L.sf = (it.y & 0x80000000u) ? SF_RMODE : 0u;
+            L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
+            L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
+            S.u_prompt = S.u_completion = S.u_total = 0;
+            L.busy = true;
+            if (L.p < L.pe) L.win = ldcg16(P.out, L.p);
+        }
+        while (__any_sync(FULL, L.busy)) {
+            #pragma unroll 1
+            for (int round = 0; round < ROUNDS; round++) {
+                v2_round(P, T, L, S);
+                if (L.busy && L.p >= L.pe) {
+                    if (v2_finish_line(P, L, S)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
+                    L.p = L.pe = 0;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- split pipeline, stage 3: early termination
+// One thread per segment: cut the segment's runs after the terminating chunk and mark the connection finished
+// (everything after it is never read by the reference, mcp/agent.go:235-242 and :169).
+__global__ void sse_finalize_kernel(const KParams P) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n_segs) return;
+    const uint32_t trec = P.seg_term[s];
+    if (trec == SSE_NONE) return;
+    const uint32_t tframe = P.recs[trec].frame;
+    sse_seg_result r = P.seg_results[s];
+    sse_run *run = &r.run;
+    for (;;) {
+        if (trec >= run->rec_first && trec < run->rec_first + run->rec_count) {
+            run->rec_count = trec - run->rec_first + 1;
+            run->frame_count = tframe - run->frame_first + 1;
+            run->next = SSE_NONE;
+            break;
+        }
+        if (run->next == SSE_NONE) break;
+        run = &P.runs[run->next];
+    }
+    r.flags |= SSE_SEG_TERMINATED;
+    r.carry_len = 0;
+    P.seg_results[s] = r;
+    ConnState ns; ns.carry_len = 0; ns.flags = CONN_FINISHED;
+    P.conns[P.segs[s].conn] = ns;
 }
 
 DfaTables *g_tables_dev[16] = { nullptr };
@@ -816,6 +914,8 @@ int sse_v2_prepare(int device) {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(sse_stream_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem2));
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(sse_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
+    if (e != cudaSuccess) return (int)e;
     g_tables_dev[device] = d;
     return 0;
 }
@@ -825,5 +925,14 @@ int sse_launch_stream_kernel_v2(const KParams &p, void *stream, int sm_count, in
     int need = (int)((p.n_segs + V2_WARPS - 1) / V2_WARPS);
     if (need < grid) grid = need > 0 ? need : 1;
     sse_stream_kernel_v2<<<grid, V2_WARPS * 32, sizeof(CtaSmem2), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
+    return (int)cudaGetLastError();
+}
+
+int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int device) {
+    sse_decode_kernel<<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const int tpb = 256;
+    sse_finalize_kernel<<<(p.n_segs + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
