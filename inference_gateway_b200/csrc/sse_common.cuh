@@ -410,7 +410,13 @@ __device__ __noinline__ uint32_t classify_finish(const uint8_t *s, int n) {
 }
 
 // ---------------------------------------------------------------- the decoder (one lane per line)
+// Deferred unquote jobs of one lane: drained warp-cooperatively (warp_unquote) instead of byte-by-byte on one lane.
+struct UnquoteJob { uint32_t s, e, dst, pad; uint32_t *patch; };
+constexpr int MAX_JOBS = 5;
+struct LaneJobs { uint32_t n; uint32_t pad; UnquoteJob j[MAX_JOBS]; };
+
 struct ParseCtx {
+    LaneJobs *jobs = nullptr;   // optional: where to queue unquote work
     const uint8_t *sm;     // warp window
     const KParams *P;
     const Schema *S;
@@ -421,7 +427,7 @@ struct Span { uint32_t off, len; bool text; };
 
 // dec: 0 = the raw bytes are the decoded string; 1 = has escapes; 2 (or 3) = may also hold invalid UTF-8, which
 // Go replaces by U+FFFD (1 byte -> 3). Decoding is single pass into a bound-sized text-arena allocation.
-__device__ __noinline__ Span capture(const ParseCtx &cx, int s, int e, int dec) {
+__device__ __noinline__ Span capture(const ParseCtx &cx, int s, int e, int dec, uint32_t *patch = nullptr) {
     Span r;
     if (!dec && cx.emitted) { r.off = (uint32_t)(cx.out_delta + s); r.len = (uint32_t)(e - s); r.text = false; return r; }
     const uint32_t raw = (uint32_t)(e - s);
@@ -431,9 +437,69 @@ __device__ __noinline__ Span capture(const ParseCtx &cx, int s, int e, int dec) 
     uint32_t o = atomicAdd(&cx.P->ctr->text_bytes, bound);
     if (o + bound > cx.P->cap_text) { atomicExch(&cx.P->ctr->status, (int)SSE_ERR_OVERFLOW); return r; }
     r.off = o;
+    if (dec && patch && cx.jobs && cx.jobs->n < (uint32_t)MAX_JOBS) {
+        // the decoded length is patched into *patch when the warp drains the queue; raw > 0 implies decoded > 0
+        UnquoteJob &j = cx.jobs->j[cx.jobs->n++];
+        j.s = (uint32_t)s; j.e = (uint32_t)e; j.dst = o; j.patch = patch;
+        r.len = raw;
+        return r;
+    }
     if (dec) r.len = json_unquote_write(cx.sm, s, e, cx.P->text + o);
     else { for (int i = s; i < e; i++) cx.P->text[o + (i - s)] = cx.sm[i]; r.len = raw; }
     return r;
+}
+
+// Warp-cooperative unquote (same result as json_unquote_write): runs of plain bytes are copied 32 at a time, the byte that
+// stops a run (escape or non-ASCII sequence) is handled by lane 0 with the exact decode.go rules.
+__device__ __noinline__ void warp_unquote(const uint8_t *__restrict__ src, uint32_t s, uint32_t e, uint8_t *__restrict__ dst, uint32_t *patch) {
+    const uint32_t lane = lane_id();
+    uint32_t i = s, n = 0;
+    while (i < e) {
+        const uint32_t idx = i + lane;
+        const uint32_t c = idx < e ? (uint32_t)src[idx] : 0x5Cu;
+        const unsigned m = __ballot_sync(FULL, idx >= e || c == '\\' || c >= 0x80);
+        const uint32_t run = m ? (uint32_t)(__ffs(m) - 1) : 32u;
+        if (lane < run) dst[n + lane] = (uint8_t)c;
+        n += run; i += run;
+        if (i < e && run < 32u) {
+            uint32_t ni = i, nn = n;
+            if (lane == 0) {
+                const uint32_t c0 = src[i];
+                if (c0 == '\\') {
+                    const uint32_t esc = src[i + 1];
+                    ni = i + 2;
+                    uint32_t r;
+                    switch (esc) {
+                    case 'b': r = 8; break;
+                    case 'f': r = 12; break;
+                    case 'n': r = 10; break;
+                    case 'r': r = 13; break;
+                    case 't': r = 9; break;
+                    case 'u': {
+                        r = (uint32_t)hex4(src + ni);
+                        ni += 4;
+                        if (r >= 0xD800 && r < 0xE000) {
+                            int r1 = -1;
+                            if (ni + 6 <= e && src[ni] == '\\' && src[ni + 1] == 'u') r1 = hex4(src + ni + 2);
+                            if (r < 0xDC00 && r1 >= 0xDC00 && r1 < 0xE000) { r = 0x10000 + ((r - 0xD800) << 10) + ((uint32_t)r1 - 0xDC00); ni += 6; }
+                            else r = 0xFFFD;
+                        }
+                        break;
+                    }
+                    default: r = esc; break;
+                    }
+                    nn += put_rune(dst, nn, r);
+                } else {
+                    const int k = utf8_valid_len(src + i, (int)(e - i));
+                    if (k == 0) { nn += put_rune(dst, nn, 0xFFFD); ni = i + 1; }
+                    else { for (int q = 0; q < k; q++) dst[nn + q] = src[i + q]; nn += k; ni = i + k; }
+                }
+            }
+            i = __shfl_sync(FULL, ni, 0); n = __shfl_sync(FULL, nn, 0);
+        }
+    }
+    if (lane == 0) *patch = n;
+    __syncwarp();
 }
 
 struct PendingTc {

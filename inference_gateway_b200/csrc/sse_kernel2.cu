@@ -93,16 +93,17 @@ __device__ __forceinline__ void value_done(Lane &L) {
     L.st = ((bits >> (d & 63u)) & 1ull) ? (uint32_t)S_AFTA : (uint32_t)S_AFTO;
 }
 
-__device__ void v2_flush_tc(const KParams &P, Lane &L, LaneScratch &S) {
-    ParseCtx cx; cx.sm = P.out; cx.P = &P; cx.S = nullptr; cx.emitted = true; cx.out_delta = 0;
-    Span id = capture(cx, (int)S.id_off, (int)(S.id_off + S.id_len), S.tc_dec & 3);
-    Span ty = capture(cx, (int)S.type_off, (int)(S.type_off + S.type_len), (S.tc_dec >> 2) & 3);
-    Span nm = capture(cx, (int)S.name_off, (int)(S.name_off + S.name_len), (S.tc_dec >> 4) & 3);
-    Span ar = capture(cx, (int)S.args_off, (int)(S.args_off + S.args_len), (S.tc_dec >> 6) & 3);
-    if ((S.tc_flags & SSE_TC_HAS_ID) || ((S.tc_flags & SSE_TC_HAS_FUNC) && (nm.len || ar.len))) L.sf |= SF_TCVALID;
+__device__ void v2_flush_tc(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
+    if ((S.tc_flags & SSE_TC_HAS_ID) || ((S.tc_flags & SSE_TC_HAS_FUNC) && (S.name_len || S.args_len))) L.sf |= SF_TCVALID;
     L.sf &= ~SF_TCOPEN;
     uint32_t idx = atomicAdd(&P.ctr->n_tcs, 1u);
     if (idx >= P.cap_tcs) { atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW); return; }
+    sse_tc *rec = &P.tcs[idx];
+    ParseCtx cx; cx.jobs = J; cx.sm = P.out; cx.P = &P; cx.S = nullptr; cx.emitted = true; cx.out_delta = 0;
+    Span id = capture(cx, (int)S.id_off, (int)(S.id_off + S.id_len), S.tc_dec & 3, &rec->id_len);
+    Span ty = capture(cx, (int)S.type_off, (int)(S.type_off + S.type_len), (S.tc_dec >> 2) & 3, &rec->type_len);
+    Span nm = capture(cx, (int)S.name_off, (int)(S.name_off + S.name_len), (S.tc_dec >> 4) & 3, &rec->name_len);
+    Span ar = capture(cx, (int)S.args_off, (int)(S.args_off + S.args_len), (S.tc_dec >> 6) & 3, &rec->args_len);
     sse_tc o;
     o.index = S.tc_index;
     o.flags = S.tc_flags | (id.text ? SSE_TC_ID_TEXT : 0) | (ty.text ? SSE_TC_TYPE_TEXT : 0) |
@@ -110,19 +111,19 @@ __device__ void v2_flush_tc(const KParams &P, Lane &L, LaneScratch &S) {
     o.next = SSE_NONE;
     o.id_off = id.off; o.id_len = id.len; o.type_off = ty.off; o.type_len = ty.len;
     o.name_off = nm.off; o.name_len = nm.len; o.args_off = ar.off; o.args_len = ar.len;
-    P.tcs[idx] = o;
+    *rec = o;            // queued unquote jobs overwrite the *_len fields when the warp drains them
     if (L.tc_first == SSE_NONE) L.tc_first = idx; else P.tcs[L.tc_prev].next = idx;
     L.tc_prev = idx;
 }
 
-__device__ void v2_elem_begin(const KParams &P, Lane &L, LaneScratch &S) {
+__device__ void v2_elem_begin(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
     if (L.skip > 0) { L.cur = TY_SKIP; return; }
     uint32_t nd = lane_top(L);
     if (nd == A_CHOICES) { L.choices_count++; L.cur = TY_STRUCT | (N_CHOICE << 4); }
     else if (nd == A_TOOLCALLS) {
         L.cur = TY_STRUCT | (N_TC << 4);
         if (lane_live(L)) {
-            if (L.sf & SF_TCOPEN) v2_flush_tc(P, L, S);
+            if (L.sf & SF_TCOPEN) v2_flush_tc(P, L, S, J);
             L.sf |= SF_TCOPEN; L.tc_count++;
             S.tc_index = 0; S.tc_flags = 0; S.tc_dec = 0;
             S.id_off = S.id_len = S.type_off = S.type_len = S.name_off = S.name_len = S.args_off = S.args_len = 0;
@@ -175,7 +176,7 @@ __device__ void v2_number_end(const KParams &P, Lane &L, LaneScratch &S, uint32_
 }
 
 // returns true when the current byte has to be looked up again in the new state
-__device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, uint32_t t) {
+__device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J, uint32_t t) {
     switch (t) {
     case A_OPEN_OBJ: case A_OPEN_ARR: {
         const bool arr = t == A_OPEN_ARR;
@@ -215,7 +216,7 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
             const uint32_t node = lane_top(L);
             L.sd--;
             if (node == A_CHOICES) L.n_choices = L.choices_count;
-            else if (node == A_TOOLCALLS) { if (lane_live(L) && (L.sf & SF_TCOPEN)) v2_flush_tc(P, L, S); }
+            else if (node == A_TOOLCALLS) { if (lane_live(L) && (L.sf & SF_TCOPEN)) v2_flush_tc(P, L, S, J); }
             else if (node == N_GOOGLE) { if (L.sf & SF_GBAD) L.sf |= SF_TYPE; }
         }
         value_done(L);
@@ -284,8 +285,8 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
         return false;
     }
     case A_LIT_NULL: v2_null(L, S); value_done(L); return false;
-    case A_ELEM_REDO: v2_elem_begin(P, L, S); L.st = S_VAL; return true;
-    case A_COMMA_ARR: v2_elem_begin(P, L, S); L.st = S_VAL; return false;
+    case A_ELEM_REDO: v2_elem_begin(P, L, S, J); L.st = S_VAL; return true;
+    case A_COMMA_ARR: v2_elem_begin(P, L, S, J); L.st = S_VAL; return false;
     default:   // A_ERR
         L.sf |= SF_SYN; L.p = L.pe - 1; L.st = S_END;
         return false;
@@ -293,7 +294,7 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
 }
 
 // A line retires: final syntax check, record, termination bookkeeping (agent.go:205-242).
-__device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S) {
+__device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
     bool terminates = false;
     if (!(L.sf & SF_SYN)) {
         if (L.depth == 0 && (L.st == S_NZERO || L.st == S_NINT || L.st == S_NFRAC || L.st == S_NEXP)) {
@@ -317,8 +318,9 @@ __device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S) {
             } else atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW);
         }
         if (L.n_choices > 0) {
-            ParseCtx cx; cx.sm = P.out; cx.P = &P; cx.S = nullptr; cx.emitted = true; cx.out_delta = 0;
-            Span ct = capture(cx, (int)L.content_off, (int)(L.content_off + L.content_len), ((L.sf & SF_CDEC) ? 1 : 0) | ((L.sf & SF_CBAD) ? 2 : 0));
+            ParseCtx cx; cx.jobs = J; cx.sm = P.out; cx.P = &P; cx.S = nullptr; cx.emitted = true; cx.out_delta = 0;
+            Span ct = capture(cx, (int)L.content_off, (int)(L.content_off + L.content_len), ((L.sf & SF_CDEC) ? 1 : 0) | ((L.sf & SF_CBAD) ? 2 : 0),
+                              &P.recs[L.rec].content_len);
             r.content_off = ct.len ? ct.off : 0; r.content_len = ct.len;
             if (ct.text && ct.len) r.flags |= SSE_F_CONTENT_TEXT;
             r.flags |= L.finish << SSE_F_FINISH_SHIFT;
@@ -365,7 +367,7 @@ __device__ void v2_finalize_segment(const KParams &P, SegSlot &sl) {
 }
 
 // One round of the per-lane automaton: KSTEPS plain steps, then the pending action (if any) of every lane.
-__device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S) {
+__device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J) {
     uint32_t pend = 0;                       // action | cls << 8 | in_str << 16 | in_tok << 17
     #pragma unroll
     for (int k = 0; k < KSTEPS; k++) {
@@ -408,7 +410,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
         uint32_t t = pend & 0xFFu;
         const uint32_t cls = (pend >> 8) & 0xFFu;
         for (;;) {
-            if (!v2_action(P, T, L, S, t)) break;            // the action chose the next state
+            if (!v2_action(P, T, L, S, J, t)) break;         // the action chose the next state
             t = T.tr[L.st * NCLS + cls];                     // redo: same byte, new state
             if (t < A_FIRST) { L.st = t; break; }
         }
@@ -782,10 +784,10 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
         // every lane that stopped at an action runs it (all lanes dispatch together: the divergent part is shared)
         #pragma unroll 1
         for (int round = 0; round < ROUNDS; round++) {
-            v2_round(P, T, L, S);
+            v2_round(P, T, L, S, nullptr);
             if (L.busy && L.p >= L.pe) {
                 SegSlot &sl = W.slots[L.slot];
-                if (v2_finish_line(P, L, S)) atomicMin(&sl.term, ((unsigned long long)L.rec << 32) | L.frame);
+                if (v2_finish_line(P, L, S, nullptr)) atomicMin(&sl.term, ((unsigned long long)L.rec << 32) | L.frame);
                 __threadfence_block();
                 if (atomicSub(&sl.pending, 1) == 1) v2_finalize_segment(P, sl);
                 L.p = L.pe = 0;
@@ -804,7 +806,9 @@ constexpr int V3_WARPS = 24;
 struct CtaSmem3 {
     DfaTables T;
     LaneScratch ls[V3_WARPS * 32];
+    LaneJobs jobs[V3_WARPS * 32];
 };
+static_assert(sizeof(CtaSmem3) <= 227 * 1024, "shared memory budget");
 
 __global__ void __launch_bounds__(V3_WARPS * 32, 1)
 sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
@@ -818,6 +822,9 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
     __syncthreads();
     const DfaTables &T = cs.T;
     LaneScratch &S = cs.ls[threadIdx.x];
+    LaneJobs *J = &cs.jobs[threadIdx.x];
+    LaneJobs *Jw = &cs.jobs[threadIdx.x & ~31u];   // this warp's 32 queues
+    J->n = 0;
     const uint32_t lane = lane_id();
     const uint32_t n_items = min(P.ctr->n_items, P.cap_items);
 
@@ -847,11 +854,27 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
         while (__any_sync(FULL, L.busy)) {
             #pragma unroll 1
             for (int round = 0; round < ROUNDS; round++) {
-                v2_round(P, T, L, S);
+                v2_round(P, T, L, S, J);
                 if (L.busy && L.p >= L.pe) {
-                    if (v2_finish_line(P, L, S)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
+                    if (v2_finish_line(P, L, S, J)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
                     L.p = L.pe = 0;
                 }
+                // strings that need unquoting were queued by the lanes: decode them with the whole warp
+                __syncwarp();
+                unsigned jm = __ballot_sync(FULL, J->n > 0);
+                while (jm) {
+                    const int leader = __ffs(jm) - 1;
+                    jm &= jm - 1;
+                    LaneJobs &LJ = Jw[leader];
+                    const uint32_t nj = LJ.n;
+                    for (uint32_t k = 0; k < nj; k++) {
+                        const UnquoteJob jb = LJ.j[k];
+                        warp_unquote(P.out, jb.s, jb.e, P.text + jb.dst, jb.patch);
+                    }
+                    __syncwarp();
+                    if ((int)lane == leader) LJ.n = 0;
+                }
+                __syncwarp();
             }
         }
     }
