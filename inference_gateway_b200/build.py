@@ -32,7 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-cudart", "static",
-           "-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
+           "-o", LIB] + os.environ.get("SSE_NVCC_DEFS", "").split() + [os.path.join(CSRC, f) for f in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

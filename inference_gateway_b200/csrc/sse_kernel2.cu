@@ -25,8 +25,14 @@ constexpr int V2_WARPS = 16;
 constexpr int V2_BUF = 6144;       // line window per warp
 constexpr int RING = 128;          // work items per warp
 constexpr int SEGSLOTS = 8;        // segments in flight per warp
-constexpr int ROUNDS = 4;          // rounds between refills
-constexpr int KSTEPS = 4;          // plain automaton steps per round before the pending actions run
+#ifndef SSE_ROUNDS
+#define SSE_ROUNDS 8
+#endif
+#ifndef SSE_KSTEPS
+#define SSE_KSTEPS 2
+#endif
+constexpr int ROUNDS = SSE_ROUNDS;   // rounds between refills / busy checks
+constexpr int KSTEPS = SSE_KSTEPS;   // plain automaton steps per round before the pending actions run
 
 struct SegSlot {
     unsigned long long term;       // min over terminating lines of (rec << 32 | frame); ~0ull: none
@@ -392,13 +398,11 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
             const uint32_t c = (w >> ((L.p & 3u) * 8u)) & 0xFFu;
             const uint32_t e = T.clssym[c];
             const uint32_t cls = e & 63u;
-            const bool in_str = (L.st - S_KSTR) < 12u || L.st >= S_V8_1;
-            const bool in_tok = in_str || (L.st - S_NMINUS) < 8u;
+            const bool in_str = L.st >= S_KSTR, in_tok = L.st >= S_NMINUS;
             const uint32_t t = T.tr[L.st * NCLS + cls];
             if (t < A_FIRST) {
                 L.km = in_str ? (uint32_t)T.kt[L.km * NSYM + ((e >> 8) & 31u)] : (uint32_t)TRIE_ROOT;
-                const uint32_t nf = (cls == C_BSLASH ? SF_ESC : 0u) | (cls >= C_H80 ? SF_HI : 0u) | ((e & CLS_UPPER) ? SF_UPPER : 0u);
-                L.sf = in_str ? (L.sf | nf) : (L.sf & ~SF_STRMASK);
+                L.sf = in_str ? (L.sf | (e >> 13)) : (L.sf & ~SF_STRMASK);
                 L.slen = in_tok ? L.slen + 1 : 0;
                 L.st = t;
                 L.p++;
@@ -801,7 +805,10 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
 // Persistent warps pull 32 work items at a time (lines of the same stream are adjacent, so the lanes of a batch walk
 // near-identical structure in lockstep); no producer code and no line window in this kernel: small instruction
 // footprint, shared memory only for the tables and the cold per-lane state.
-constexpr int V3_WARPS = 24;
+#ifndef SSE_V3_WARPS
+#define SSE_V3_WARPS 24
+#endif
+constexpr int V3_WARPS = SSE_V3_WARPS;
 
 struct CtaSmem3 {
     DfaTables T;

@@ -13,10 +13,11 @@ namespace ssetab {
 // ---- automaton states
 enum : uint8_t {
     S_VAL = 0, S_ARR0, S_OBJ0, S_KEY, S_COLON, S_AFTO, S_AFTA, S_END,
+    S_T1, S_T2, S_T3, S_F1, S_F2, S_F3, S_F4, S_N1, S_N2, S_N3,
+    // states >= S_NMINUS are inside a token (number or string); states >= S_KSTR are inside a string
+    S_NMINUS, S_NZERO, S_NINT, S_NDOT, S_NFRAC, S_NE, S_NESIGN, S_NEXP,
     S_KSTR, S_KESC, S_KU1, S_KU2, S_KU3, S_KU4,
     S_VSTR, S_VESC, S_VU1, S_VU2, S_VU3, S_VU4,
-    S_NMINUS, S_NZERO, S_NINT, S_NDOT, S_NFRAC, S_NE, S_NESIGN, S_NEXP,
-    S_T1, S_T2, S_T3, S_F1, S_F2, S_F3, S_F4, S_N1, S_N2, S_N3,
     S_V8_1, S_V8_2, S_V8_E0, S_V8_ED, S_V8_3, S_V8_F0, S_V8_F4,
     NST
 };
@@ -38,7 +39,7 @@ constexpr int NSYM = 28;          // a-z, '_', other
 constexpr int SYM_OTHER = 27;
 constexpr int NTRIE = 320;        // >= number of trie nodes (checked at build time)
 constexpr uint16_t TRIE_DEAD = 0, TRIE_ROOT = 1;
-constexpr uint16_t CLS_UPPER = 0x8000;   // clssym flag: ASCII upper-case letter
+constexpr uint16_t CLS_ESC = 0x2000, CLS_HI = 0x4000, CLS_UPPER = 0x8000;   // clssym flags: backslash, byte >= 0x80, ASCII upper-case (>> 13 gives the per-string flag bits)
 
 // schema enums (same values as sse_common.cuh)
 enum : uint8_t { TTY_SKIP, TTY_STR, TTY_PSTR, TTY_INT, TTY_F32, TTY_STRUCT, TTY_PSTRUCT, TTY_SLICE, TTY_PSLICE,
@@ -88,7 +89,7 @@ inline int build_tables(DfaTables &T, const FieldSrc *fields, int n_fields, cons
         if (c >= 'a' && c <= 'z') sym = (uint16_t)(c - 'a');
         else if (c >= 'A' && c <= 'Z') { sym = (uint16_t)(c - 'A'); up = CLS_UPPER; }
         else if (c == '_') sym = 26;
-        T.clssym[c] = (uint16_t)(k | (sym << 8) | up);
+        T.clssym[c] = (uint16_t)(k | (sym << 8) | up | (k == C_BSLASH ? CLS_ESC : 0) | (k >= C_H80 ? CLS_HI : 0));
     }
     // ---------------- automaton
     auto set = [&](int s, int c, uint8_t v) { T.tr[s * NCLS + c] = v; };
