@@ -1,0 +1,38 @@
+/*
+ * sse_gateway.h -- host-side mirror of the reference's streaming interfaces, above the C ABI of sse_gpu.h
+ * (implemented in inference_gateway_b200/csrc/sse_gateway.cpp, exported by libssegpu.so).
+ *
+ *   ssegw_stream_chat_completions   core.IProvider.StreamChatCompletions (providers/core/interfaces.go:22; provider.go:277-344)
+ *   ssegw_upstream_write / _close   response.Body bytes / EOF-or-error (provider.go:322-330)
+ *   ssegw_pump                      one tick of the per-GPU batcher
+ *   ssegw_recv                      `line, ok := <-streamCh` (api/routes.go:602-606, mcp/agent.go:171)
+ *   ssegw_agent_recv and friends    mcp.Agent.RunWithStream for one iteration (mcp/agent.go:126-290, final [DONE] :140-143)
+ */
+#ifndef SSE_GATEWAY_H
+#define SSE_GATEWAY_H
+#include "sse_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ssegw ssegw;
+
+ssegw *ssegw_new(int device, uint32_t max_conns, uint32_t bytes_per_batch, int *status);
+void   ssegw_free(ssegw *g);
+int    ssegw_stream_chat_completions(ssegw *g, uint8_t mode);
+size_t ssegw_upstream_write(ssegw *g, int stream, const uint8_t *data, size_t n);
+void   ssegw_upstream_close(ssegw *g, int stream);
+int    ssegw_pump(ssegw *g);
+int    ssegw_recv(ssegw *g, int stream, uint8_t *buf, size_t cap, size_t *n);
+void   ssegw_release_stream(ssegw *g, int stream);
+int    ssegw_agent_recv(ssegw *g, int stream, uint8_t *buf, size_t cap, size_t *n);
+sse_bytes ssegw_agent_content(ssegw *g, int stream);
+int    ssegw_agent_has_tool_calls(ssegw *g, int stream);
+int    ssegw_agent_terminated(ssegw *g, int stream, int *finish);
+size_t ssegw_agent_tool_calls(ssegw *g, int stream, sse_tool_call *calls, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -12,9 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = open(os.path.join(ROOT, "include", "sse_gpu.h")).read()
 
 
-def declared_functions():
-    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
-    return sorted(set(re.findall(r"\b(sse_[a-z_0-9]+)\s*\(", body)))
+GW_HEADER = open(os.path.join(ROOT, "include", "sse_gateway.h")).read()
+
+
+def declared_functions(text=None, prefix="sse_"):
+    body = re.sub(r"/\*.*?\*/", "", text or HEADER, flags=re.S)
+    return sorted(set(re.findall(r"\b(%s[a-z_0-9]+)\s*\(" % prefix, body)))
 
 
 def test_exports_every_declared_symbol():
@@ -25,6 +28,10 @@ def test_exports_every_declared_symbol():
         assert hasattr(L, n), f"{n} is declared in include/sse_gpu.h but not exported by libssegpu.so"
     assert set(names) == set(A.EXPORTS)
     assert L.sse_abi_version() == 1
+    gw = declared_functions(GW_HEADER, "ssegw_")
+    assert len(gw) >= 12
+    for n in gw:
+        assert hasattr(L, n), f"{n} is declared in include/sse_gateway.h but not exported"
 
 
 def test_struct_layouts_match_header():

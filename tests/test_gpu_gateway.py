@@ -1,0 +1,102 @@
+"""GPU: the reference's own streaming tests, re-stated against the host-side mirror of its interfaces
+(include/sse_gateway.h). Each test cites the Go test it follows; inputs are the reference's fixtures."""
+import json
+import os
+
+import pytest
+
+from inference_gateway_b200 import _abi as A
+from inference_gateway_b200.gateway import Gateway
+
+pytestmark = pytest.mark.gpu
+GOLD = {f["name"]: f for f in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_fixtures.json")))["fixtures"]}
+R = A.MODE_R | A.MODE_PARSE
+
+
+@pytest.fixture(scope="module")
+def gw():
+    g = Gateway(device=0, max_conns=64, bytes_per_batch=1 << 20)
+    yield g
+    g.close()
+
+
+def run_agent_iteration(gw, elements, cut=None):
+    """mockProvider.StreamChatCompletions returns a channel fed with `elements`; the agent forwards to the middleware
+    channel. Here the elements arrive as upstream bytes (each followed by '\\n'), optionally cut into odd pieces."""
+    sid = gw.stream_chat_completions(R)
+    body = ("\n".join(elements) + "\n").encode()
+    pieces = [body] if not cut else [body[i:i + cut] for i in range(0, len(body), cut)]
+    out = []
+    for p in pieces:
+        assert gw.upstream_write(sid, p) == len(p)
+        gw.pump()
+        while True:
+            e = gw.agent_recv(sid)
+            if e is None:
+                break
+            out.append(e)
+    gw.upstream_close(sid)
+    gw.pump()
+    try:
+        while True:
+            e = gw.agent_recv(sid)
+            if e is None:
+                break
+            out.append(e)
+    except EOFError:
+        pass
+    state = gw.agent_state(sid)
+    gw.release(sid)
+    return out, state
+
+
+@pytest.mark.parametrize("cut", [None, 37])
+def test_agent_run_with_stream_no_tool_calls(gw, cut):
+    """tests/mcp_agent_test.go:522-598 "no tool calls streaming": chunks are forwarded, the concatenated delta.content is
+    "Hello there!", the stream ends with one [DONE]."""
+    fx = GOLD["agent_no_tool_calls"]
+    out, (content, has_tc, term, fin, calls) = run_agent_iteration(gw, fx["iterations"][0], cut)
+    assert content.decode() == "Hello there!"
+    assert not has_tc and calls == [] and term and fin == 1
+    assert out[-1] == b"data: [DONE]\n\n" and sum(e == b"data: [DONE]\n\n" for e in out) == 1
+    assert len(out) == 5 and all(e.startswith(b"data: {") and e.endswith(b"\n\n") for e in out[:-1])
+    joined = b"".join(json.loads(e[6:])["choices"][0]["delta"].get("content", "").encode() for e in out[:-1])
+    assert joined == b"Hello there!"
+
+
+@pytest.mark.parametrize("cut", [None, 101])
+def test_agent_run_with_stream_two_iterations(gw, cut):
+    """tests/mcp_agent_test.go:665-862: iteration 1 ends with finish_reason tool_calls and two parsed calls whose
+    arguments are {"param":"value"} and {"action":"execute"} (:745-750); iteration 2 ends with stop."""
+    fx = GOLD["agent_two_iterations_tool_calls"]
+    out1, (c1, has1, term1, fin1, calls1) = run_agent_iteration(gw, fx["iterations"][0], cut)
+    assert c1.decode() == "I'll use both tools to help you." and has1 and term1 and fin1 == 2
+    assert [(c["id"], c["name"], json.loads(c["args"])) for c in calls1] == [
+        (b"call_123", b"mcp_test_tool", {"param": "value"}), (b"call_456", b"mcp_other_tool", {"action": "execute"})]
+    out2, (c2, has2, term2, fin2, calls2) = run_agent_iteration(gw, fx["iterations"][1], cut)
+    assert c2.decode() == "Based on the tool results, both tools executed successfully!" and not has2 and fin2 == 1
+    assert calls2 == []
+    # the middleware writes every iteration's frames and the single terminal frame of the last one (mcp.go:253-299)
+    assert out2[-1] == b"data: [DONE]\n\n"
+
+
+def test_provider_channel_passthrough_and_backpressure(gw):
+    """provider.go:307-340: one element per '\\n'-terminated line including the newline; the unterminated tail is dropped at
+    EOF; a full channel (100 elements) stops accepting upstream bytes until the receiver drains it."""
+    sid = gw.stream_chat_completions(A.MODE_P)
+    assert gw.upstream_write(sid, b"data: a\n\ndata: b") == 16
+    gw.pump()
+    assert gw.recv(sid) == b"data: a\n" and gw.recv(sid) == b"\n" and gw.recv(sid) is None
+    assert gw.upstream_write(sid, b"\n" * 150) == 150
+    gw.pump()
+    assert gw.upstream_write(sid, b"x\n") == 0            # 151 elements queued: back-pressure
+    got = []
+    while (e := gw.recv(sid)) is not None:
+        got.append(e)
+    assert got[0] == b"data: b\n" and len(got) == 150
+    assert gw.upstream_write(sid, b"tail without newline") == 20
+    gw.upstream_close(sid)
+    gw.pump()
+    with pytest.raises(EOFError):
+        gw.recv(sid)
+    gw.release(sid)
