@@ -27,24 +27,24 @@ def run_agent_iteration(gw, elements, cut=None):
     body = ("\n".join(elements) + "\n").encode()
     pieces = [body] if not cut else [body[i:i + cut] for i in range(0, len(body), cut)]
     out = []
+
+    def drain():
+        try:
+            while True:
+                e = gw.agent_recv(sid)
+                if e is None:
+                    return
+                out.append(e)
+        except EOFError:      # middleware channel closed: the iteration is over (after the single [DONE])
+            return
+
     for p in pieces:
-        assert gw.upstream_write(sid, p) == len(p)
-        gw.pump()
-        while True:
-            e = gw.agent_recv(sid)
-            if e is None:
-                break
-            out.append(e)
+        if gw.upstream_write(sid, p) == len(p):
+            gw.pump()
+        drain()
     gw.upstream_close(sid)
     gw.pump()
-    try:
-        while True:
-            e = gw.agent_recv(sid)
-            if e is None:
-                break
-            out.append(e)
-    except EOFError:
-        pass
+    drain()
     state = gw.agent_state(sid)
     gw.release(sid)
     return out, state
