@@ -32,7 +32,8 @@ struct Counters {
     int32_t  status;
     uint32_t n_items;      // split pipeline: work items written by the produce kernel
     uint32_t item_ticket;  // split pipeline: next item batch for the decode kernel
-    uint32_t pad[5];
+    uint32_t n_deps;       // split pipeline: dependent lines (derived from the previous line's parse)
+    uint32_t pad[4];
 };
 
 struct KParams {
@@ -56,6 +57,8 @@ struct KParams {
     // split pipeline (produce -> decode -> finalize)
     uint4 *items;            uint32_t cap_items;   // src, len | rmode << 31, rec, seg
     uint32_t *seg_term;                            // per segment: smallest terminating record index, SSE_NONE if none
+    uint2 *item_deps;                              // per item: first dependent, count
+    uint4 *deps;             uint32_t cap_deps;    // src, len, rec, cp | cs << 16 (common prefix / suffix with the previous line)
 };
 
 // launch wrappers (sse_kernel.cu)

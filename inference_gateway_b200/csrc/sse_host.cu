@@ -42,6 +42,7 @@ struct Slot {
     sse_usage *d_usages = nullptr; uint8_t *d_text = nullptr; sse_run *d_runs = nullptr; sse_seg_result *d_segres = nullptr;
     Counters *d_ctr = nullptr;
     uint4 *d_items = nullptr; uint32_t *d_segterm = nullptr;   // split pipeline scratch (device only)
+    uint2 *d_itemdeps = nullptr; uint4 *d_deps = nullptr;
     uint32_t n_segs = 0, in_bytes = 0;
 };
 
@@ -72,7 +73,7 @@ void free_slot(Slot &s) {
     cudaFreeHost(s.h_tcs); cudaFreeHost(s.h_usages); cudaFreeHost(s.h_text); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_segres);
     cudaFreeHost(s.h_ctr);
     cudaFree(s.d_in); cudaFree(s.d_segs); cudaFree(s.d_out); cudaFree(s.d_frames); cudaFree(s.d_recs); cudaFree(s.d_tcs);
-    cudaFree(s.d_usages); cudaFree(s.d_text); cudaFree(s.d_runs); cudaFree(s.d_segres); cudaFree(s.d_ctr); cudaFree(s.d_items); cudaFree(s.d_segterm);
+    cudaFree(s.d_usages); cudaFree(s.d_text); cudaFree(s.d_runs); cudaFree(s.d_segres); cudaFree(s.d_ctr); cudaFree(s.d_items); cudaFree(s.d_segterm); cudaFree(s.d_itemdeps); cudaFree(s.d_deps);
 }
 
 KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
@@ -88,6 +89,7 @@ KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
     p.runs = s.d_runs; p.cap_runs = c->cfg.max_runs;
     p.seg_results = s.d_segres; p.ctr = s.d_ctr;
     p.items = s.d_items; p.cap_items = c->cfg.max_recs; p.seg_term = s.d_segterm;
+    p.item_deps = s.d_itemdeps; p.deps = s.d_deps; p.cap_deps = c->cfg.max_recs;
     return p;
 }
 
@@ -233,6 +235,7 @@ int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
         ok = ok && dalloc(s.d_tcs, cfg->max_tcs) && dalloc(s.d_usages, cfg->max_usages) && dalloc(s.d_text, cfg->text_arena_bytes);
         ok = ok && dalloc(s.d_runs, cfg->max_runs) && dalloc(s.d_segres, cfg->max_segs) && dalloc(s.d_ctr, 1);
         ok = ok && dalloc(s.d_items, cfg->max_recs) && dalloc(s.d_segterm, cfg->max_segs);
+        ok = ok && dalloc(s.d_itemdeps, cfg->max_recs) && dalloc(s.d_deps, cfg->max_recs);
     }
     if (!ok) { sse_destroy(c); return SSE_ERR_CUDA; }
     *out = c;

@@ -125,6 +125,7 @@ sse_stream_kernel(const KParams P) {
                         uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
                         nlm = eqmask16(v, 0x0A0A0A0Au);
                         if (mode & SSE_MODE_R) brm = eqmask16(v, 0x5B5B5B5Bu);
+                        if (SPLIT && (mode & SSE_MODE_PARSE)) W.spec[off >> 4] = (uint16_t)special_bits16(v);
                         // mask bytes outside [pos, fill)
                         uint32_t valid = 0xFFFFu;
                         if (off < pos) valid &= 0xFFFFu << (pos - off);
@@ -206,27 +207,45 @@ sse_stream_kernel(const KParams P) {
                     pre_b[h] = tot_b + sb - vb; pre_f[h] = tot_f + sf - vf; pre_r[h] = tot_r + sr - vr;
                     tot_b += __shfl_sync(FULL, sb, 31); tot_f += __shfl_sync(FULL, sf, 31); tot_r += __shfl_sync(FULL, sr, 31);
                 }
-                uint32_t my_q = 0;
+                // split pipeline: chains. A line that differs from the previous decoded line of this round only by plain
+                // string bytes becomes a dependent of it (its record is derived by the decode kernel, not re-decoded).
+                uint32_t tot_q = 0, tot_d = 0, qb = 0, db = 0;
                 if (SPLIT) {
-                    #pragma unroll
-                    for (int h = 0; h < 2; h++) my_q += (my_parse[h] && my_kind[h] == K_EMIT) ? 1u : 0u;
-                }
-                uint32_t pre_q = my_q, tot_q = 0, qb = 0;
-                if (SPLIT) {
-                    #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, pre_q, d); if ((int)lane >= d) pre_q += t; }
-                    tot_q = __shfl_sync(FULL, pre_q, 31);
-                    pre_q -= my_q;
+                    int prev = -1, cur_head = -1;
+                    uint32_t cur_deps = 0;
+                    for (int i = 0; i < n_lines; i++) {
+                        const LineEnt e = W.lt[i];
+                        if (!(e.parse && e.kind == K_EMIT)) continue;
+                        bool dep = false; int cp = 0, cs = 0;
+                        if (prev >= 0) {
+                            const LineEnt pe = W.lt[prev];
+                            dep = chain_compare(buf, W.spec, e.pay_s, e.pay_e - e.pay_s, pe.pay_s, pe.pay_e - pe.pay_s, cp, cs);
+                        }
+                        if (lane == 0) {
+                            LineEnt &w = W.lt[i];
+                            if (dep) { w.chain = 1; w.cp = (uint16_t)cp; w.cs = (uint16_t)cs; w.rel = (uint16_t)tot_d; }
+                            else {
+                                if (cur_head >= 0) W.lt[cur_head].ndeps = (uint16_t)cur_deps;
+                                w.chain = 0; w.rel = (uint16_t)tot_q; w.dfirst = (uint16_t)tot_d; w.ndeps = 0;
+                            }
+                        }
+                        if (dep) { tot_d++; cur_deps++; } else { tot_q++; cur_head = i; cur_deps = 0; }
+                        prev = i;
+                    }
+                    if (lane == 0 && cur_head >= 0) W.lt[cur_head].ndeps = (uint16_t)cur_deps;
+                    __syncwarp();
                 }
                 uint32_t ob = 0, fb = 0, rb = 0;
                 if (lane == 0) {
                     if (SPLIT && tot_q) qb = atomicAdd(&P.ctr->n_items, tot_q);
+                    if (SPLIT && tot_d) db = atomicAdd(&P.ctr->n_deps, tot_d);
                     if (tot_b) ob = atomicAdd(&P.ctr->out_bytes, (tot_b + 15u) & ~15u);
                     if (tot_f) fb = atomicAdd(&P.ctr->n_frames, tot_f);
                     if (tot_r) rb = atomicAdd(&P.ctr->n_recs, tot_r);
                 }
-                ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0); qb = __shfl_sync(FULL, qb, 0);
-                if (ob + tot_b + 16 > P.cap_out || fb + tot_f > P.cap_frames || rb + tot_r > P.cap_recs || (SPLIT && qb + tot_q > P.cap_items)) {
+                ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0); qb = __shfl_sync(FULL, qb, 0); db = __shfl_sync(FULL, db, 0);
+                if (ob + tot_b + 16 > P.cap_out || fb + tot_f > P.cap_frames || rb + tot_r > P.cap_recs ||
+                    (SPLIT && (qb + tot_q > P.cap_items || db + tot_d > P.cap_deps))) {
                     if (lane == 0) atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW);
                     overflow = true; break;
                 }
@@ -262,17 +281,23 @@ sse_stream_kernel(const KParams P) {
                         cx.emitted = my_kind[h] == K_EMIT;
                         cx.out_delta = (int64_t)(ob + pre_b[h]) - (int64_t)e.src_s;
                         if (SPLIT && my_kind[h] == K_EMIT) {
-                            // lane order within the round: items of lane L (h = 0 then h = 1) follow those of lanes < L
-                            const uint32_t qi = qb + pre_q + ((h == 1 && my_parse[0] && my_kind[0] == K_EMIT) ? 1u : 0u);
                             sse_rec stub;
                             stub.frame = fb + pre_f[h]; stub.flags = 0; stub.content_off = stub.content_len = 0; stub.tc_first = SSE_NONE;
                             stub.tc_count = 0; stub.n_choices = 0; stub.usage = SSE_NONE; stub.payload_len = (uint32_t)(e.pay_e - e.pay_s);
                             P.recs[rb + pre_r[h]] = stub;
                             uint4 it;
                             it.x = ob + pre_b[h] + (uint32_t)(e.pay_s - e.src_s);
-                            it.y = (uint32_t)(e.pay_e - e.pay_s) | ((mode & SSE_MODE_R) ? 0x80000000u : 0u);
-                            it.z = rb + pre_r[h]; it.w = s;
-                            P.items[qi] = it;
+                            it.z = rb + pre_r[h];
+                            if (e.chain == 0) {
+                                it.y = (uint32_t)(e.pay_e - e.pay_s) | ((mode & SSE_MODE_R) ? 0x80000000u : 0u);
+                                it.w = s;
+                                P.items[qb + e.rel] = it;
+                                P.item_deps[qb + e.rel] = make_uint2(db + e.dfirst, e.ndeps);
+                            } else {
+                                it.y = (uint32_t)(e.pay_e - e.pay_s);
+                                it.w = (uint32_t)e.cp | ((uint32_t)e.cs << 16);
+                                P.deps[db + e.rel] = it;
+                            }
                             continue;
                         }
                         ParseOut po;

@@ -47,6 +47,12 @@ struct LaneScratch {               // cold per-lane state (usage ints, the tool-
     uint32_t tc_flags, tc_dec;
     uint32_t id_off, id_len, type_off, type_len, name_off, name_len, args_off, args_len;
 };
+// Template of the last decoded line of a chain (split pipeline): what a dependent line's record is derived from.
+struct LaneTpl {
+    sse_rec rec;
+    uint32_t ok, vs, ve, len, run_cp, run_cs, pad0, pad1;   // content span [vs, ve) relative to the payload start
+};
+
 struct WarpSmem2 {
     alignas(16) uint8_t buf[V2_BUF + 16];
     LineEnt lt[LT_MAX];
@@ -68,7 +74,7 @@ static_assert(sizeof(CtaSmem2) <= 227 * 1024, "shared memory budget");
 // per-string flags (cleared outside strings) and per-line flags
 constexpr uint32_t SF_ESC = 1, SF_HI = 2, SF_UPPER = 4, SF_BAD = 8, SF_STRMASK = 15;
 constexpr uint32_t SF_SYN = 0x100, SF_TYPE = 0x200, SF_DEPTH = 0x400, SF_GBAD = 0x800, SF_USAGE = 0x1000,
-                   SF_TCNONNIL = 0x2000, SF_TCOPEN = 0x4000, SF_TCVALID = 0x8000, SF_CDEC = 0x10000, SF_RMODE = 0x20000, SF_CBAD = 0x40000;
+                   SF_TCNONNIL = 0x2000, SF_TCOPEN = 0x4000, SF_TCVALID = 0x8000, SF_CDEC = 0x10000, SF_RMODE = 0x20000, SF_CBAD = 0x40000, SF_CSET = 0x80000;
 
 struct Lane {
     uint32_t p, pe;                // out-arena offsets of the payload being decoded
@@ -77,14 +83,10 @@ struct Lane {
     unsigned long long ct, ct1, sstk;   // container-type bit stack (1 = array), 128 levels
     uint32_t content_off, content_len, tc_count, tc_first, tc_prev;
     uint32_t rec, frame, slot, plen;
+    uint32_t dep_first, dep_cnt;       // split pipeline: dependents of the line being decoded
     bool busy;
 };
 
-// 0x80 in every byte of w that is '"', '\\', < 0x20 or >= 0x80 (exact for the lowest flagged byte)
-__device__ __forceinline__ uint32_t special_mask4(uint32_t w) {
-    const uint32_t q = w ^ 0x22222222u, b = w ^ 0x5C5C5C5Cu;
-    return (((q - 0x01010101u) & ~q) | ((b - 0x01010101u) & ~b) | ((w - 0x20202020u) & ~w) | w) & 0x80808080u;
-}
 __device__ __forceinline__ uint4 ldcg16(const uint8_t *base, uint32_t off) {
     return __ldcg(reinterpret_cast<const uint4 *>(base + (off & ~15u)));
 }
@@ -146,7 +148,7 @@ __device__ void v2_null(Lane &L, LaneScratch &S) {
     switch (tgt) {
     case TG_CHOICES:
         L.n_choices = 0; L.choices_count = 0; L.finish = SSE_FIN_NONE; L.content_off = L.content_len = 0;
-        L.sf &= ~(SF_CDEC | SF_CBAD | SF_TCNONNIL | SF_TCOPEN | SF_TCVALID);
+        L.sf &= ~(SF_CDEC | SF_CBAD | SF_CSET | SF_TCNONNIL | SF_TCOPEN | SF_TCVALID);
         L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
         break;
     case TG_USAGE: L.sf &= ~SF_USAGE; S.u_prompt = S.u_completion = S.u_total = 0; break;
@@ -258,7 +260,7 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
                 switch (tgt) {
                 case TG_CONTENT:
                     L.content_off = start; L.content_len = len;
-                    L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
+                    L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | SF_CSET | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
                     break;
                 case TG_FINISH:
                     if (len == 0) L.finish = SSE_FIN_NONE;
@@ -300,7 +302,7 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
 }
 
 // A line retires: final syntax check, record, termination bookkeeping (agent.go:205-242).
-__device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
+__device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J, LaneTpl *tp = nullptr) {
     bool terminates = false;
     if (!(L.sf & SF_SYN)) {
         if (L.depth == 0 && (L.st == S_NZERO || L.st == S_NINT || L.st == S_NFRAC || L.st == S_NEXP)) {
@@ -342,6 +344,14 @@ __device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJo
     }
     r.payload_len = L.plen;
     P.recs[L.rec] = r;
+    if (tp) {
+        // a line is a usable template when its only captured value is an unescaped content string
+        tp->ok = (r.flags & SSE_F_JSON_OK) && L.n_choices > 0 && (L.sf & SF_CSET) && !(L.sf & (SF_CDEC | SF_CBAD | SF_TCNONNIL | SF_USAGE)) &&
+                 L.tc_count == 0 && !terminates;
+        tp->rec = r;
+        tp->vs = L.content_off - (L.pe - L.plen); tp->ve = tp->vs + L.content_len; tp->len = L.plen;
+        tp->run_cp = tp->run_cs = 0xFFFFFFFFu;
+    }
     L.busy = false;
     return terminates;
 }
@@ -458,7 +468,7 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
     Lane L; L.busy = false; L.p = L.pe = 0; L.win = make_uint4(0, 0, 0, 0);
     L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.km = TRIE_ROOT; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
     L.finish = 0; L.ct = L.ct1 = L.sstk = 0; L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
-    L.rec = L.frame = L.slot = L.plen = 0;
+    L.rec = L.frame = L.slot = L.plen = 0; L.dep_first = L.dep_cnt = 0;
 
     Producer pr; pr.phase = 0; pr.more = true;
     uint32_t head = 0, tail = 0;     // ring indices (warp-uniform registers mirror of W.ring_*)
@@ -814,6 +824,7 @@ struct CtaSmem3 {
     DfaTables T;
     LaneScratch ls[V3_WARPS * 32];
     LaneJobs jobs[V3_WARPS * 32];
+    LaneTpl tpl[V3_WARPS * 32];
 };
 static_assert(sizeof(CtaSmem3) <= 227 * 1024, "shared memory budget");
 
@@ -830,6 +841,7 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
     const DfaTables &T = cs.T;
     LaneScratch &S = cs.ls[threadIdx.x];
     LaneJobs *J = &cs.jobs[threadIdx.x];
+    LaneTpl &Tp = cs.tpl[threadIdx.x];
     LaneJobs *Jw = &cs.jobs[threadIdx.x & ~31u];   // this warp's 32 queues
     J->n = 0;
     const uint32_t lane = lane_id();
@@ -838,7 +850,7 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
     Lane L; L.busy = false; L.p = L.pe = 0; L.win = make_uint4(0, 0, 0, 0);
     L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.km = TRIE_ROOT; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
     L.finish = 0; L.ct = L.ct1 = L.sstk = 0; L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
-    L.rec = L.frame = L.slot = L.plen = 0;
+    L.rec = L.frame = L.slot = L.plen = 0; L.dep_first = L.dep_cnt = 0;
 
     for (;;) {
         uint32_t base = 0;
@@ -850,6 +862,7 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
             const uint4 it = P.items[idx];
             L.p = it.x; L.plen = it.y & 0x7FFFFFFFu; L.pe = it.x + L.plen; L.rec = it.z; L.slot = it.w;   // slot: segment index
             L.frame = P.recs[it.z].frame;
+            { const uint2 dd = P.item_deps[idx]; L.dep_first = dd.x; L.dep_cnt = dd.y; }
             L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.km = TRIE_ROOT; L.slen = 0;
             L.sf = (it.y & 0x80000000u) ? SF_RMODE : 0u;
             L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
@@ -863,8 +876,33 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
             for (int round = 0; round < ROUNDS; round++) {
                 v2_round(P, T, L, S, J);
                 if (L.busy && L.p >= L.pe) {
-                    if (v2_finish_line(P, L, S, J)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
+                    if (v2_finish_line(P, L, S, J, &Tp)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
                     L.p = L.pe = 0;
+                    // dependents: lines that differ from their predecessor only by plain string bytes (chain_compare). If the
+                    // difference lies inside the template's content string, the record is the template's with the content span
+                    // moved; otherwise the line is decoded and becomes the template for the rest of the chain.
+                    while (L.dep_cnt) {
+                        const uint4 d = P.deps[L.dep_first];
+                        L.dep_first++; L.dep_cnt--;
+                        Tp.run_cp = min(Tp.run_cp, d.w & 0xFFFFu); Tp.run_cs = min(Tp.run_cs, d.w >> 16);
+                        if (Tp.ok && Tp.run_cp >= Tp.vs && Tp.len - Tp.run_cs <= Tp.ve) {
+                            sse_rec r = Tp.rec;
+                            r.frame = P.recs[d.z].frame;
+                            r.content_off = d.x + Tp.vs; r.content_len = d.y - Tp.len + (Tp.ve - Tp.vs);
+                            r.payload_len = d.y;
+                            P.recs[d.z] = r;
+                        } else {
+                            L.p = d.x; L.plen = d.y; L.pe = d.x + d.y; L.rec = d.z; L.frame = P.recs[d.z].frame;
+                            L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.km = TRIE_ROOT; L.slen = 0;
+                            L.sf &= SF_RMODE;
+                            L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
+                            L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
+                            S.u_prompt = S.u_completion = S.u_total = 0;
+                            L.busy = true;
+                            if (L.p < L.pe) L.win = ldcg16(P.out, L.p);
+                            break;
+                        }
+                    }
                 }
                 // strings that need unquoting were queued by the lanes: decode them with the whole warp
                 __syncwarp();

@@ -228,3 +228,37 @@ def test_product_does_not_use_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert "import oracle" not in src and "from oracle" not in src and "sse_oracle" not in src, f
+
+
+# ------------------------------------------------------------------ chains of near-identical lines (split pipeline)
+def test_line_chains(engine):
+    """Consecutive chunks that differ only inside the content string are derived from the previous parse; every other
+    kind of difference has to fall back to a full decode. All of it must stay bit-exact."""
+    env = '{"id":"chatcmpl-%s","object":"chat.completion.chunk","created":%s,"model":"m","choices":[{"index":0,"delta":{%s},"finish_reason":%s}]%s}'
+
+    def ev(content=None, cid="abc123", created="1700000000", fin="null", tail="", extra=""):
+        delta = extra + ('"content":"%s"' % content if content is not None else "")
+        return ("data: " + env % (cid, created, delta, fin, tail) + "\n\n").encode()
+
+    streams = [
+        # plain content deltas of different lengths (the common case)
+        b"".join(ev(w) for w in ["Hello", " there", ", this is a much longer piece of plain content that spans more than sixteen bytes",
+                                 "", "x", " and some more words to keep the chain going for a while", "!"]) + ev(fin='"stop"'),
+        # identical consecutive lines, then a line that only differs in `created`, then in the id
+        ev("same") + ev("same") + ev("same", created="1700000001") + ev("same", cid="abc124") + ev("other"),
+        # escapes, quotes, unicode and control escapes inside the content break the chain at that line only
+        ev("plain one") + ev('with \\"quotes\\"') + ev("plain two") + ev("café") + ev("plain three") + ev("tab\\tchar") + ev("plain four"),
+        # the difference extends past the content string (finish_reason changes, usage appears)
+        ev("a") + ev("b", fin='"length"') + ev("c") + ev("d", tail=',"usage":{"prompt_tokens":1,"completion_tokens":2,"total_tokens":3}') + ev("e"),
+        # tool-call argument fragments: plain differences inside `arguments`, not inside content
+        b"".join(ev(None, extra='"tool_calls":[{"index":0,"function":{"arguments":"%s"}}]' % a) for a in ["abc", "defgh", "i", "jklmnopqrstuvwxyz0123456789"]),
+        # content key twice, role key present, content null
+        ev("x", extra='"content":"first",') + ev("y", extra='"content":"first",') + ev("z", extra='"role":"assistant",') + ev("w", extra='"role":"assistant",'),
+        # very long plain content (several windows of skip) and a chain across it
+        ev("p" * 3000) + ev("q" * 2500) + ev("r" * 10) + ev("s" * 3500),
+        # invalid JSON lines in a chain
+        ev("ok") + b'data: {"choices":[{"delta":{"content":"broken"}}\n\n' + b'data: {"choices":[{"delta":{"content":"brokeN"}}\n\n' + ev("ok again"),
+    ]
+    for m in (R, PP):
+        for nb in (1, 2, 5):
+            _run_and_check(engine, streams, [m] * len(streams), n_batches=nb, seed=40 + nb)
