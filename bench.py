@@ -45,10 +45,10 @@ def env_int(name, default):
         return default
 
 
-def build_workload(n_streams: int, shard: int, workload: str):
+def build_workload(n_streams: int, shard: int, workload: str, n_content=None):
     from inference_gateway_b200 import synth
     t0 = time.time()
-    streams, mode = synth.make_config(workload, n_streams=n_streams, shard=shard)
+    streams, mode = synth.make_config(workload, n_streams=n_streams, shard=shard, n_content=n_content)
     bodies = [b for b, _, _ in streams]
     n_events = sum(n for _, n, _ in streams)
     log(f"[bench] rank shard {shard}: generated {len(bodies)} streams, {sum(map(len, bodies)) / 1e6:.1f} MB, "
@@ -69,7 +69,7 @@ def fill_slot(eng, arena, segs, bodies, mode):
     segs["in_off"][:len(bodies)] = offs.astype(np.uint32)
     segs["in_len"][:len(bodies)] = lens.astype(np.uint32)
     segs["mode"][:len(bodies)] = mode
-    segs["provider"][:len(bodies)] = 0
+    segs["provider"][:len(bodies)] = np.arange(len(bodies), dtype=np.uint8) % 4   # the connection's provider (flavours cycle cohere/groq/anthropic/ollama)
     segs["reserved"][:len(bodies)] = 0
     return len(bodies), total, int(lens.sum())
 
@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--streams", type=int, default=65536, help="concurrent streams per GPU")
     ap.add_argument("--workload", default="C4")
     ap.add_argument("--mode", type=int, default=None, help="override the workload's mode bits (0 P, 2 P+parse, 3 R+parse)")
+    ap.add_argument("--flags", type=int, default=0, help="sse_config.flags (1 v1 kernel, 2 fused v2 kernel, 4 chains experiment)")
+    ap.add_argument("--n-content", type=int, default=None, help="content deltas per stream (default: the config's 7)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -185,11 +187,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from inference_gateway_b200 import SseEngine, shard as sh
-    bodies, mode, n_events = build_workload(args.streams, rank, args.workload)
+    bodies, mode, n_events = build_workload(args.streams, rank, args.workload, args.n_content)
     if args.mode is not None:
         mode = args.mode
     in_payload = sum(map(len, bodies))
-    eng = SseEngine(device=local_rank, max_conns=len(bodies), bytes_per_batch=in_payload, n_slots=N_SLOTS, carry_slot_bytes=16384)
+    eng = SseEngine(device=local_rank, max_conns=len(bodies), bytes_per_batch=in_payload, n_slots=N_SLOTS, carry_slot_bytes=16384, flags=args.flags)
     # a non-default torch stream: its handle is passed to the library so that the kernels, the resets and the
     # CUDA events of the timed region all live on the same stream (handle 0 would mean "library stream")
     tstream = torch.cuda.Stream()

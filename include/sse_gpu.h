@@ -68,6 +68,8 @@ typedef struct {
 } sse_config;
 
 #define SSE_FLAG_KERNEL_V1 1u  /* fused first-generation kernel (sequential per-lane decoder) */
+#define SSE_FLAG_CHAINS 4u     /* split pipeline, experimental: derive the record of a line that differs from the previous decoded
+                                  line only by plain bytes inside the content string, and group decode work by line shape */
 #define SSE_FLAG_KERNEL_V2 2u  /* fused producer/consumer kernel (table-driven automaton); default is the split pipeline */
 
 /* One segment = the bytes read from ONE connection since the previous batch. in_off is 16-byte aligned. */
@@ -166,6 +168,7 @@ typedef struct {
     const uint8_t        *text;     /* decoded strings */
     const sse_run        *runs;
     const sse_seg_result *segs;
+    uint32_t n_decoded, n_derived;  /* statistics: lines decoded by the automaton / derived from the previous line's parse */
 } sse_result;
 
 typedef struct {

@@ -125,7 +125,7 @@ sse_stream_kernel(const KParams P) {
                         uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
                         nlm = eqmask16(v, 0x0A0A0A0Au);
                         if (mode & SSE_MODE_R) brm = eqmask16(v, 0x5B5B5B5Bu);
-                        if (SPLIT && (mode & SSE_MODE_PARSE)) W.spec[off >> 4] = (uint16_t)special_bits16(v);
+                        if (SPLIT && (mode & SSE_MODE_PARSE) && (P.flags & SSE_FLAG_CHAINS)) W.spec[off >> 4] = (uint16_t)special_bits16(v);
                         // mask bytes outside [pos, fill)
                         uint32_t valid = 0xFFFFu;
                         if (off < pos) valid &= 0xFFFFu << (pos - off);
@@ -210,7 +210,26 @@ sse_stream_kernel(const KParams P) {
                 // split pipeline: chains. A line that differs from the previous decoded line of this round only by plain
                 // string bytes becomes a dependent of it (its record is derived by the decode kernel, not re-decoded).
                 uint32_t tot_q = 0, tot_d = 0, qb = 0, db = 0;
-                if (SPLIT) {
+                if (SPLIT && !(P.flags & SSE_FLAG_CHAINS)) {
+                    // every decoded line is its own work item: index = rank among this round's emitted data lines
+                    uint32_t my_q = 0;
+                    #pragma unroll
+                    for (int h = 0; h < 2; h++) my_q += (my_parse[h] && my_kind[h] == K_EMIT) ? 1u : 0u;
+                    uint32_t pre_q = my_q;
+                    #pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, pre_q, d); if ((int)lane >= d) pre_q += t; }
+                    tot_q = __shfl_sync(FULL, pre_q, 31);
+                    pre_q -= my_q;
+                    #pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        int i = (int)lane + 32 * h;
+                        if (i < n_lines && my_parse[h] && my_kind[h] == K_EMIT) {
+                            LineEnt &w = W.lt[i];
+                            w.chain = 0; w.rel = (uint16_t)(pre_q + ((h == 1 && my_parse[0] && my_kind[0] == K_EMIT) ? 1u : 0u)); w.dfirst = 0; w.ndeps = 0;
+                        }
+                    }
+                    __syncwarp();
+                } else if (SPLIT) {
                     int prev = -1, cur_head = -1;
                     uint32_t cur_deps = 0;
                     for (int i = 0; i < n_lines; i++) {
@@ -289,10 +308,14 @@ sse_stream_kernel(const KParams P) {
                             it.x = ob + pre_b[h] + (uint32_t)(e.pay_s - e.src_s);
                             it.z = rb + pre_r[h];
                             if (e.chain == 0) {
-                                it.y = (uint32_t)(e.pay_e - e.pay_s) | ((mode & SSE_MODE_R) ? 0x80000000u : 0u);
+                                // shape class; the second decoded line of a round (first content delta, the longest) sorts first: long work early
+                                const uint32_t ord = min((uint32_t)e.rel, 7u);
+                                const uint32_t cls = ((ord == 1u ? 0u : (ord == 0u ? 1u : ord)) << 2) | (seg.provider & 3u);
+                                it.y = (uint32_t)(e.pay_e - e.pay_s) | (cls << 24) | ((mode & SSE_MODE_R) ? 0x80000000u : 0u);
                                 it.w = s;
+                                if (P.flags & SSE_FLAG_CHAINS) atomicAdd(&P.ctr->class_count[cls], 1u);
                                 P.items[qb + e.rel] = it;
-                                P.item_deps[qb + e.rel] = make_uint2(db + e.dfirst, e.ndeps);
+                                if (P.flags & SSE_FLAG_CHAINS) P.item_deps[qb + e.rel] = make_uint2(db + e.dfirst, e.ndeps);
                             } else {
                                 it.y = (uint32_t)(e.pay_e - e.pay_s);
                                 it.w = (uint32_t)e.cp | ((uint32_t)e.cs << 16);

@@ -87,6 +87,7 @@ struct Lane {
     bool busy;
 };
 
+__device__ __forceinline__ void prefetch_l2(const uint8_t *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ uint4 ldcg16(const uint8_t *base, uint32_t off) {
     return __ldcg(reinterpret_cast<const uint4 *>(base + (off & ~15u)));
 }
@@ -846,6 +847,7 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
     J->n = 0;
     const uint32_t lane = lane_id();
     const uint32_t n_items = min(P.ctr->n_items, P.cap_items);
+    const bool chains = (P.flags & SSE_FLAG_CHAINS) != 0;
 
     Lane L; L.busy = false; L.p = L.pe = 0; L.win = make_uint4(0, 0, 0, 0);
     L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.km = TRIE_ROOT; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
@@ -859,24 +861,30 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
         if (base >= n_items) break;
         const uint32_t idx = base + lane;
         if (idx < n_items) {
-            const uint4 it = P.items[idx];
-            L.p = it.x; L.plen = it.y & 0x7FFFFFFFu; L.pe = it.x + L.plen; L.rec = it.z; L.slot = it.w;   // slot: segment index
+            const bool sorted = (P.flags & SSE_FLAG_CHAINS) != 0;
+            const uint4 it = sorted ? P.items_sorted[idx] : P.items[idx];
+            L.p = it.x; L.plen = it.y & 0x00FFFFFFu; L.pe = it.x + L.plen; L.rec = it.z; L.slot = it.w;   // slot: segment index
             L.frame = P.recs[it.z].frame;
-            { const uint2 dd = P.item_deps[idx]; L.dep_first = dd.x; L.dep_cnt = dd.y; }
+            L.dep_first = L.dep_cnt = 0;
+            if (sorted) { const uint2 dd = P.item_deps_sorted[idx]; L.dep_first = dd.x; L.dep_cnt = dd.y; if (dd.y) prefetch_l2(reinterpret_cast<const uint8_t *>(&P.deps[dd.x])); }
             L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.km = TRIE_ROOT; L.slen = 0;
             L.sf = (it.y & 0x80000000u) ? SF_RMODE : 0u;
             L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
             L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
             S.u_prompt = S.u_completion = S.u_total = 0;
             L.busy = true;
-            if (L.p < L.pe) L.win = ldcg16(P.out, L.p);
+            if (L.p < L.pe) {
+                L.win = ldcg16(P.out, L.p);
+                // items are grouped by shape, not by address: pull the rest of the payload towards L2 ahead of the automaton
+                if (sorted) for (uint32_t q = (L.p & ~127u) + 128u; q < L.pe && q < L.p + 1024u; q += 128u) prefetch_l2(P.out + q);
+            }
         }
         while (__any_sync(FULL, L.busy)) {
             #pragma unroll 1
             for (int round = 0; round < ROUNDS; round++) {
                 v2_round(P, T, L, S, J);
                 if (L.busy && L.p >= L.pe) {
-                    if (v2_finish_line(P, L, S, J, &Tp)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
+                    if (v2_finish_line(P, L, S, J, chains ? &Tp : nullptr)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
                     L.p = L.pe = 0;
                     // dependents: lines that differ from their predecessor only by plain string bytes (chain_compare). If the
                     // difference lies inside the template's content string, the record is the template's with the content span
@@ -886,12 +894,16 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
                         L.dep_first++; L.dep_cnt--;
                         Tp.run_cp = min(Tp.run_cp, d.w & 0xFFFFu); Tp.run_cs = min(Tp.run_cs, d.w >> 16);
                         if (Tp.ok && Tp.run_cp >= Tp.vs && Tp.len - Tp.run_cs <= Tp.ve) {
+                            // the stub already holds the frame index: write the other 28 bytes without reading it back
                             sse_rec r = Tp.rec;
-                            r.frame = P.recs[d.z].frame;
                             r.content_off = d.x + Tp.vs; r.content_len = d.y - Tp.len + (Tp.ve - Tp.vs);
                             r.payload_len = d.y;
-                            P.recs[d.z] = r;
+                            uint32_t *dst = reinterpret_cast<uint32_t *>(&P.recs[d.z]);
+                            dst[1] = r.flags;
+                            *reinterpret_cast<uint2 *>(dst + 2) = make_uint2(r.content_off, r.content_len);
+                            *reinterpret_cast<uint4 *>(dst + 4) = make_uint4(r.tc_first, (uint32_t)r.tc_count | ((uint32_t)r.n_choices << 16), r.usage, r.payload_len);
                         } else {
+                            atomicAdd(&P.ctr->n_dep_decoded, 1u);
                             L.p = d.x; L.plen = d.y; L.pe = d.x + d.y; L.rec = d.z; L.frame = P.recs[d.z].frame;
                             L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.km = TRIE_ROOT; L.slen = 0;
                             L.sf &= SF_RMODE;
@@ -922,6 +934,27 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
                 __syncwarp();
             }
         }
+    }
+}
+
+
+// ---------------------------------------------------------------- split pipeline, stage 1b: group items by shape class
+// (counting sort, 32 classes: provider x position of the line among its round's decoded lines). Lanes of a decode batch then
+// walk lines of the same shape and share the divergent parts of the automaton.
+__global__ void sse_class_scan_kernel(const KParams P) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t run = 0;
+        for (int c = 0; c < 32; c++) { P.ctr->class_cursor[c] = run; run += P.ctr->class_count[c]; }
+    }
+}
+__global__ void sse_class_scatter_kernel(const KParams P) {
+    const uint32_t n = min(P.ctr->n_items, P.cap_items);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 it = P.items[i];
+        const uint32_t cls = (it.y >> 24) & 31u;
+        const uint32_t pos = atomicAdd(&P.ctr->class_cursor[cls], 1u);
+        P.items_sorted[pos] = it;
+        P.item_deps_sorted[pos] = P.item_deps[i];
     }
 }
 
@@ -997,6 +1030,10 @@ int sse_launch_stream_kernel_v2(const KParams &p, void *stream, int sm_count, in
 }
 
 int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int device) {
+    if (p.flags & SSE_FLAG_CHAINS) {
+        sse_class_scan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
+        sse_class_scatter_kernel<<<sm_count * 4, 256, 0, (cudaStream_t)stream>>>(p);
+    }
     sse_decode_kernel<<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
