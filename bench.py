@@ -83,7 +83,7 @@ class ClockSampler:
         self.idx = gpu_index
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.p = None
 
@@ -159,7 +159,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=65536, help="concurrent streams per GPU")
@@ -311,7 +311,8 @@ def main():
     except (OSError, ValueError):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "sse_stream_kernel",
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "split pipeline: sse_stream_kernel<produce> + sse_decode_kernel + sse_finalize_kernel (whole step)",
                 "alg_bytes_per_launch": alg_bytes, "kernel_ms": 1e3 * kern_s,
                 "hbm_read_frac": counts["in_bytes"] / kern_s / 1e9 / peak}
 

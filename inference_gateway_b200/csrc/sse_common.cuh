@@ -102,8 +102,9 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // 4-bit mask of the bytes of w equal to the byte replicated in pat
 __device__ __forceinline__ uint32_t eqmask4(uint32_t w, uint32_t pat) {
-    uint32_t c = __vcmpeq4(w, pat) & 0x01010101u;
-    return ((c * 0x00204081u) >> 21) & 0xFu;
+    const uint32_t x = w ^ pat;                                             // zero byte <=> equal
+    const uint32_t z = ~((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x)) & 0x80808080u;   // exact: 0x80 where the byte of x is zero
+    return (((z >> 7) * 0x00204081u) >> 21) & 0xFu;
 }
 __device__ __forceinline__ uint32_t eqmask16(const uint4 &v, uint32_t pat) {
     return eqmask4(v.x, pat) | (eqmask4(v.y, pat) << 4) | (eqmask4(v.z, pat) << 8) | (eqmask4(v.w, pat) << 12);
