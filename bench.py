@@ -225,6 +225,15 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
+    # nvidia-smi needs a few hundred ms before its first sample: keep the GPU under the same load (untimed) meanwhile,
+    # so that the clock samples bracket the timed region and are all taken under load
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < 0.6:
+        step()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     launches0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
