@@ -169,7 +169,14 @@ typedef struct {
     const sse_run        *runs;
     const sse_seg_result *segs;
     uint32_t n_decoded, n_derived;  /* statistics: lines decoded by the automaton / derived from the previous line's parse */
+    uint32_t overflow;              /* SSE_OVF_* bits when status == SSE_ERR_OVERFLOW: which sse_config capacity to raise */
 } sse_result;
+
+#define SSE_OVF_OUT    0x01u  /* out_arena_bytes / max_frames / max_recs (bump-allocated together per round) */
+#define SSE_OVF_TCS    0x02u  /* max_tcs */
+#define SSE_OVF_USAGES 0x04u  /* max_usages */
+#define SSE_OVF_TEXT   0x08u  /* text_arena_bytes */
+#define SSE_OVF_RUNS   0x10u  /* max_runs */
 
 typedef struct {
     uint8_t *in_arena;     /* pinned; caller writes each segment's bytes at a 16-byte aligned in_off */

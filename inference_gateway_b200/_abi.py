@@ -65,7 +65,7 @@ class Result(C.Structure):
                 ("out", C.POINTER(C.c_uint8)), ("frames", C.POINTER(Frame)), ("recs", C.POINTER(Rec)),
                 ("tcs", C.POINTER(Tc)), ("usages", C.POINTER(Usage)), ("text", C.POINTER(C.c_uint8)),
                 ("runs", C.POINTER(Run)), ("segs", C.POINTER(SegResult)),
-                ("n_decoded", C.c_uint32), ("n_derived", C.c_uint32)]
+                ("n_decoded", C.c_uint32), ("n_derived", C.c_uint32), ("overflow", C.c_uint32)]
 
 
 class Batch(C.Structure):

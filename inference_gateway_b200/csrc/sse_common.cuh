@@ -531,7 +531,7 @@ __device__ __noinline__ Span capture(const ParseCtx &cx, int s, int e, int dec, 
     if (raw == 0) return r;
     const uint32_t bound = (((dec & 2) ? 3u * raw : raw) + 3u) & ~3u;   // 4-byte aligned allocations
     uint32_t o = atomicAdd(&cx.P->ctr->text_bytes, bound);
-    if (o + bound > cx.P->cap_text) { atomicExch(&cx.P->ctr->status, (int)SSE_ERR_OVERFLOW); return r; }
+    if (o + bound > cx.P->cap_text) { sse_overflow(cx.P->ctr, SSE_OVF_TEXT); return r; }
     r.off = o;
     if (dec && patch && cx.jobs && cx.jobs->n < (uint32_t)MAX_JOBS) {
         // the decoded length is patched into *patch when the warp drains the queue; raw > 0 implies decoded > 0
@@ -616,7 +616,7 @@ __device__ __noinline__ void flush_tc(const ParseCtx &cx, PendingTc &t, uint32_t
     Span id = cap(t.id, t.dec & 1), ty = cap(t.type, t.dec & 2), nm = cap(t.name, t.dec & 4), ar = cap(t.args, t.dec & 8);
     if ((t.flags & SSE_TC_HAS_ID) || ((t.flags & SSE_TC_HAS_FUNC) && (nm.len || ar.len))) tc_valid = true;
     uint32_t idx = atomicAdd(&cx.P->ctr->n_tcs, 1u);
-    if (idx >= cx.P->cap_tcs) { atomicExch(&cx.P->ctr->status, (int)SSE_ERR_OVERFLOW); return; }
+    if (idx >= cx.P->cap_tcs) { sse_overflow(cx.P->ctr, SSE_OVF_TCS); return; }
     sse_tc o;
     o.index = t.index;
     o.flags = t.flags | (id.text ? SSE_TC_ID_TEXT : 0) | (ty.text ? SSE_TC_TYPE_TEXT : 0) |
@@ -846,7 +846,7 @@ __device__ __noinline__ void decode_chunk(const ParseCtx &cx, int p, int pe, Par
             sse_usage u; u.prompt_tokens = u_prompt; u.completion_tokens = u_completion; u.total_tokens = u_total;
             cx.P->usages[idx] = u;
             out.usage = idx; out.flags |= SSE_F_HAS_USAGE;
-        } else atomicExch(&cx.P->ctr->status, (int)SSE_ERR_OVERFLOW);
+        } else sse_overflow(cx.P->ctr, SSE_OVF_USAGES);
     }
     if (n_choices > 0) {
         Span ct = capture(cx, (int)(content_sp >> 16), (int)(content_sp & 0xFFFF), content_dec ? 3 : 0);
@@ -912,7 +912,7 @@ __device__ __noinline__ void append_run(const KParams &P, RunChain &rc, uint32_t
     uint32_t idx = 0;
     if (lane_id() == 0) idx = atomicAdd(&P.ctr->n_runs, 1u);
     idx = __shfl_sync(FULL, idx, 0);
-    if (idx >= P.cap_runs) { if (lane_id() == 0) atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW); return; }
+    if (idx >= P.cap_runs) { if (lane_id() == 0) sse_overflow(P.ctr, SSE_OVF_RUNS); return; }
     if (lane_id() == 0) {
         sse_run r; r.frame_first = ff; r.frame_count = fc; r.rec_first = rf; r.rec_count = rcnt; r.next = SSE_NONE;
         P.runs[idx] = r;
@@ -949,7 +949,7 @@ __device__ __noinline__ bool process_long_line(const KParams &P, RunChain &rc, c
     }
     ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0);
     bool ovf = (nf && (ob + (uint32_t)flen > P.cap_out || fb >= P.cap_frames)) || (nr && rb >= P.cap_recs);
-    if (ovf) { if (lane == 0) atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW); return false; }
+    if (ovf) { if (lane == 0) sse_overflow(P.ctr, SSE_OVF_OUT); return false; }
     if (emit) {
         if (mode & SSE_MODE_R) {
             copy_g2g_bytes(P.out + ob, line + a, b - a);

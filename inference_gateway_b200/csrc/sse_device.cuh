@@ -34,7 +34,8 @@ struct Counters {
     uint32_t item_ticket;  // split pipeline: next item batch for the decode kernel
     uint32_t n_deps;       // split pipeline: dependent lines (candidates for derivation from the previous line's parse)
     uint32_t n_dep_decoded;// ... of which the decode kernel had to decode after all
-    uint32_t pad[3];
+    uint32_t overflow;     // SSE_OVF_* bits: which arena was too small
+    uint32_t pad[2];
     uint32_t class_count[32];  // split pipeline: items per shape class (provider x position of the head in its round)
     uint32_t class_cursor[32];
 };
@@ -65,6 +66,13 @@ struct KParams {
     uint4 *items_sorted; uint2 *item_deps_sorted;  // items grouped by shape class so that the 32 lanes of a decode batch walk alike lines
     uint4 *deps;             uint32_t cap_deps;    // src, len, rec, cp | cs << 16 (common prefix / suffix with the previous line)
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void sse_overflow(Counters *c, uint32_t which) {
+    atomicOr(&c->overflow, which);
+    atomicExch(&c->status, (int)SSE_ERR_OVERFLOW);
+}
+#endif
 
 // launch wrappers (sse_kernel.cu)
 int sse_launch_stream_kernel(const KParams &p, void *stream, int sm_count);            // v1: per-lane sequential decoder

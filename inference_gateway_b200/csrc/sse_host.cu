@@ -137,6 +137,7 @@ int do_download(sse_ctx *c, Slot &s, sse_result *res, cudaStream_t st) {
     res->status = k.status;
     res->n_segs = s.n_segs;
     if (k.status != SSE_OK) {   // overflow: the batch result is unusable, report loudly
+        res->overflow = k.overflow;
         return k.status;
     }
     res->n_frames = k.n_frames; res->n_recs = k.n_recs; res->n_tcs = k.n_tcs; res->n_usages = k.n_usages;

@@ -265,7 +265,7 @@ sse_stream_kernel(const KParams P) {
                 ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0); qb = __shfl_sync(FULL, qb, 0); db = __shfl_sync(FULL, db, 0);
                 if (ob + tot_b + 16 > P.cap_out || fb + tot_f > P.cap_frames || rb + tot_r > P.cap_recs ||
                     (SPLIT && (qb + tot_q > P.cap_items || db + tot_d > P.cap_deps))) {
-                    if (lane == 0) atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW);
+                    if (lane == 0) sse_overflow(P.ctr, SSE_OVF_OUT);
                     overflow = true; break;
                 }
                 // frame table

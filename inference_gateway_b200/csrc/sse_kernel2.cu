@@ -106,7 +106,7 @@ __device__ void v2_flush_tc(const KParams &P, Lane &L, LaneScratch &S, LaneJobs 
     if ((S.tc_flags & SSE_TC_HAS_ID) || ((S.tc_flags & SSE_TC_HAS_FUNC) && (S.name_len || S.args_len))) L.sf |= SF_TCVALID;
     L.sf &= ~SF_TCOPEN;
     uint32_t idx = atomicAdd(&P.ctr->n_tcs, 1u);
-    if (idx >= P.cap_tcs) { atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW); return; }
+    if (idx >= P.cap_tcs) { sse_overflow(P.ctr, SSE_OVF_TCS); return; }
     sse_tc *rec = &P.tcs[idx];
     ParseCtx cx; cx.jobs = J; cx.sm = P.out; cx.P = &P; cx.S = nullptr; cx.emitted = true; cx.out_delta = 0;
     Span id = capture(cx, (int)S.id_off, (int)(S.id_off + S.id_len), S.tc_dec & 3, &rec->id_len);
@@ -324,7 +324,7 @@ __device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJo
             if (idx < P.cap_usages) {
                 sse_usage u; u.prompt_tokens = S.u_prompt; u.completion_tokens = S.u_completion; u.total_tokens = S.u_total;
                 P.usages[idx] = u; r.usage = idx; r.flags |= SSE_F_HAS_USAGE;
-            } else atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW);
+            } else sse_overflow(P.ctr, SSE_OVF_USAGES);
         }
         if (L.n_choices > 0) {
             ParseCtx cx; cx.jobs = J; cx.sm = P.out; cx.P = &P; cx.S = nullptr; cx.emitted = true; cx.out_delta = 0;
@@ -691,7 +691,7 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
                     }
                     ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0);
                     if (ob + tot_b + 16 > P.cap_out || fb + tot_f > P.cap_frames || rb + tot_r > P.cap_recs || fb + tot_f >= (1u << 29)) {
-                        if (lane == 0) { atomicExch(&P.ctr->status, (int)SSE_ERR_OVERFLOW); if (tot_q) atomicSub(&W.slots[pr.slot].pending, (int)tot_q); }
+                        if (lane == 0) { sse_overflow(P.ctr, SSE_OVF_OUT); if (tot_q) atomicSub(&W.slots[pr.slot].pending, (int)tot_q); }
                         pr.overflow = true; pr.phase = 3;
                     } else {
                         #pragma unroll

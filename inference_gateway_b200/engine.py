@@ -145,7 +145,10 @@ class SseEngine:
 
     def collect(self, slot) -> BatchResult:
         res = A.Result()
-        A.check(self.L.sse_collect(self._ctx, slot, C.byref(res)), "sse_collect")
+        rc = self.L.sse_collect(self._ctx, slot, C.byref(res))
+        if rc == A.SSE_ERR_OVERFLOW:
+            raise A.SseError(rc, f"sse_collect (overflow mask 0x{res.overflow:x}: 1 out/frames/recs, 2 tcs, 4 usages, 8 text, 16 runs)")
+        A.check(rc, "sse_collect")
         return self._wrap(res)
 
     def release(self, slot):
@@ -166,7 +169,10 @@ class SseEngine:
 
     def download(self, slot, stream: int = 0) -> BatchResult:
         res = A.Result()
-        A.check(self.L.sse_download(self._ctx, slot, C.byref(res), C.c_void_p(stream)), "sse_download")
+        rc = self.L.sse_download(self._ctx, slot, C.byref(res), C.c_void_p(stream))
+        if rc == A.SSE_ERR_OVERFLOW:
+            raise A.SseError(rc, f"sse_download (overflow mask 0x{res.overflow:x}: 1 out/frames/recs, 2 tcs, 4 usages, 8 text, 16 runs)")
+        A.check(rc, "sse_download")
         return self._wrap(res)
 
     def launch_count(self) -> int:
