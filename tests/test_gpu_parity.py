@@ -262,3 +262,20 @@ def test_line_chains(engine):
     for m in (R, PP):
         for nb in (1, 2, 5):
             _run_and_check(engine, streams, [m] * len(streams), n_batches=nb, seed=40 + nb)
+
+
+def test_overflow_is_reported_not_hidden():
+    """A result arena that is too small fails the batch loudly and says which capacity to raise."""
+    from inference_gateway_b200 import SseEngine
+    eng = SseEngine(device=0, max_conns=8, bytes_per_batch=1 << 16, max_frames=4, max_recs=4)
+    try:
+        body = b"data: {\"choices\":[]}\n\n" * 50
+        slot, arena, segs = eng.acquire()
+        n, nb = eng.fill(arena, segs, [(0, R, body)])
+        eng.submit(slot, n, nb)
+        with pytest.raises(A.SseError) as e:
+            eng.collect(slot)
+        assert e.value.status == A.SSE_ERR_OVERFLOW and "overflow mask 0x1" in str(e.value)
+        eng.release(slot)
+    finally:
+        eng.close()
