@@ -193,7 +193,7 @@ void sse_default_config(sse_config *cfg, uint32_t max_conns, uint32_t bytes_per_
     cfg->max_tcs = (uint32_t)(in / 256 + 1024);
     cfg->max_usages = cfg->max_recs;
     cfg->text_arena_bytes = (uint32_t)(in / 4 + 65536);
-    cfg->max_runs = max_conns + 1024;
+    cfg->max_runs = (uint32_t)(in / 2048 + max_conns + 1024);   // one extra run per window / 64 lines of a long segment
     cfg->carry_slot_bytes = 16384;
     cfg->n_slots = 2;
 }
