@@ -42,28 +42,47 @@ def _run(eng, bodies, mode):
     return slot, eng.collect(slot)
 
 
+def _per_stream(res):
+    """Total frame count / record count / emitted bytes per segment, following the extra runs of long segments."""
+    ff, fc = res.segs["frame_first"].astype(np.int64), res.segs["frame_count"].astype(np.int64)
+    rc = res.segs["rec_count"].astype(np.int64)
+    flen = res.frames["len"].astype(np.int64)
+    csum = np.concatenate([[0], np.cumsum(flen)])
+    nbytes = csum[ff + fc] - csum[ff]
+    fcount, rcount = fc.copy(), rc.copy()
+    nxt = res.segs["next"]
+    for i in np.nonzero(nxt != A.NONE)[0]:
+        j = int(nxt[i])
+        while j != A.NONE:
+            r = res.runs[j]
+            f0, fn = int(r["frame_first"]), int(r["frame_count"])
+            fcount[i] += fn; rcount[i] += int(r["rec_count"]); nbytes[i] += csum[f0 + fn] - csum[f0]
+            j = int(r["next"])
+    return fcount, rcount, nbytes
+
+
+def _joined(res, i):
+    return b"".join(res.seg_frames(i))
+
+
 def test_passthrough_is_the_identity_on_complete_lines(eng, workload):
     """Mode P at full size: per stream, the frames are exactly the '\\n'-terminated lines of the input, in order."""
     slot, res = _run(eng, workload, A.MODE_P)
     try:
-        assert int(res.raw.n_runs) == 0
-        ff, fc = res.segs["frame_first"].astype(np.int64), res.segs["frame_count"].astype(np.int64)
+        fcount, _, nbytes = _per_stream(res)
         n_lines = np.fromiter((b.count(b"\n") for b in workload), dtype=np.int64, count=N)
-        assert np.array_equal(fc, n_lines)
-        flen = res.frames["len"].astype(np.int64)
-        csum = np.concatenate([[0], np.cumsum(flen)])
-        per_stream_bytes = csum[ff + fc] - csum[ff]
+        assert np.array_equal(fcount, n_lines)
         expect = np.fromiter((b.rfind(b"\n") + 1 for b in workload), dtype=np.int64, count=N)
-        assert np.array_equal(per_stream_bytes, expect)          # unterminated tails are held back, nothing else
-        assert np.array_equal(res.segs["carry_len"].astype(np.int64), np.fromiter((len(b) for b in workload), dtype=np.int64, count=N) - expect)
-        # byte identity on a stride of streams (frames of a segment are contiguous in the out arena)
+        assert np.array_equal(nbytes, expect)                    # unterminated tails are held back, nothing else
+        total = np.fromiter((len(b) for b in workload), dtype=np.int64, count=N)
+        assert np.array_equal(res.segs["carry_len"].astype(np.int64), total - expect)
+        # byte identity on a stride of streams, and a checksum of checksums over them
+        cin = cout = 0
         for i in range(0, N, 257):
-            o = int(res.frames["off"][ff[i]])
-            assert res.out[o:o + int(expect[i])].tobytes() == workload[i][:int(expect[i])]
-        # global checksum of checksums: every emitted byte is an input byte of a complete line
-        total_in = sum(int(np.frombuffer(b[:e], dtype=np.uint8).sum(dtype=np.int64)) for b, e in zip(workload[::64], expect[::64]))
-        total_out = sum(int(res.out[int(res.frames["off"][ff[i]]):int(res.frames["off"][ff[i]]) + int(expect[i])].sum(dtype=np.int64)) for i in range(0, N, 64))
-        assert total_in == total_out
+            got = _joined(res, i)
+            assert got == workload[i][:int(expect[i])]
+            cin += sum(workload[i][:int(expect[i])]); cout += sum(got)
+        assert cin == cout
     finally:
         eng.release(slot)
 
@@ -73,49 +92,34 @@ def test_reframe_accounting_and_idempotence(eng, workload):
     input: "data: X\\n\\n" re-frames to itself); one JSON_OK record per frame; re-framing the output is the identity."""
     slot, res = _run(eng, workload, R)
     try:
-        flags = res.segs["flags"]
-        assert np.all(flags & A.SEG_TERMINATED)
-        ff, fc = res.segs["frame_first"].astype(np.int64), res.segs["frame_count"].astype(np.int64)
-        rf, rc = res.segs["rec_first"].astype(np.int64), res.segs["rec_count"].astype(np.int64)
-        assert np.array_equal(fc, rc)                              # no swallowed [DONE] before the finish chunk
-        # position of the terminating event in every input stream
-        ends = np.empty(N, dtype=np.int64)
+        assert np.all(res.segs["flags"] & A.SEG_TERMINATED)
+        fcount, rcount, nbytes = _per_stream(res)
+        assert np.array_equal(fcount, rcount)                      # no swallowed [DONE] before the finish chunk
+        ends = np.empty(N, dtype=np.int64)                         # end of the terminating event in every input stream
         n_ev = np.empty(N, dtype=np.int64)
         for i, b in enumerate(workload):
             k = b.find(b'"finish_reason":"')
             e = b.index(b"\n\n", k) + 2
             ends[i] = e
             n_ev[i] = b.count(b"\n\n", 0, e)
-        assert np.array_equal(fc, n_ev)
-        flen = res.frames["len"].astype(np.int64)
-        csum = np.concatenate([[0], np.cumsum(flen)])
-        assert np.array_equal(csum[ff + fc] - csum[ff], ends)
+        assert np.array_equal(fcount, n_ev)
+        assert np.array_equal(nbytes, ends)
         sample = list(range(0, N, 129))
-        for i in sample:
-            o = int(res.frames["off"][ff[i]])
-            assert res.out[o:o + int(ends[i])].tobytes() == workload[i][:int(ends[i])]
-        # records: all emitted chunks are valid JSON, exactly the last one terminates
+        outputs = []
         rflags = res.recs["flags"]
-        last = rf + rc - 1
-        assert np.all(rflags[last] & A.F_TERMINATES)
-        ok_per_stream = np.add.reduceat((rflags & A.F_JSON_OK).astype(np.int64), rf) if np.all(np.diff(rf) > 0) else None
-        if ok_per_stream is not None:
-            pass
-        valid = np.zeros(len(rflags), dtype=bool)
         for i in sample:
-            valid[rf[i]:rf[i] + rc[i]] = True
-        assert np.all(rflags[valid] & A.F_JSON_OK)
-        term = (rflags[valid] & A.F_TERMINATES) != 0
-        assert int(term.sum()) == len(sample)
-        outputs = [res.out[int(res.frames["off"][ff[i]]):int(res.frames["off"][ff[i]]) + int(ends[i])].tobytes() for i in sample]
+            got = _joined(res, i)
+            assert got == workload[i][:int(ends[i])]               # canonical "data: X\n\n" re-frames to itself
+            outputs.append(got)
+            recs = res.seg_recs(i)
+            assert all(rflags[r] & A.F_JSON_OK for r in recs)
+            assert [bool(rflags[r] & A.F_TERMINATES) for r in recs] == [False] * (len(recs) - 1) + [True]
     finally:
         eng.release(slot)
     # idempotence: the emitted frames are canonical SSE, so feeding them back yields the same bytes
     slot, res2 = _run(eng, outputs, R)
     try:
-        ff2, fc2 = res2.segs["frame_first"].astype(np.int64), res2.segs["frame_count"].astype(np.int64)
         for j, body in enumerate(outputs):
-            o = int(res2.frames["off"][ff2[j]])
-            assert res2.out[o:o + len(body)].tobytes() == body
+            assert _joined(res2, j) == body
     finally:
         eng.release(slot)
