@@ -19,8 +19,11 @@ namespace {
 // ---------------------------------------------------------------- the kernel
 // SPLIT = false: the complete v1 kernel. SPLIT = true: stage 1 of the split pipeline (stage, split, classify, emit;
 // one work item per emitted data line goes to P.items for sse_decode_kernel; no early termination here).
+#ifndef SSE_V1_MINB
+#define SSE_V1_MINB 2
+#endif
 template <bool SPLIT>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, SSE_V1_MINB)
 sse_stream_kernel(const KParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaSmem &cs = *reinterpret_cast<CtaSmem *>(smem_raw);
