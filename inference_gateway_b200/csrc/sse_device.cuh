@@ -20,6 +20,11 @@ struct ConnState {
 #define CONN_DEAD     2u   // line exceeded carry_slot_bytes
 #define CONN_LONG     4u   // a line longer than the smem window is being assembled in the carry slot
 
+#ifndef SSE_LEN_SHIFT
+#define SSE_LEN_SHIFT 5
+#endif
+#define SSE_LEN_BUCKETS (4096 >> SSE_LEN_SHIFT)
+#define SSE_N_BUCKETS (32 * SSE_LEN_BUCKETS)
 struct Counters {
     uint32_t ticket;       // next segment to process
     uint32_t out_bytes;
@@ -36,8 +41,9 @@ struct Counters {
     uint32_t n_dep_decoded;// ... of which the decode kernel had to decode after all
     uint32_t overflow;     // SSE_OVF_* bits: which arena was too small
     uint32_t pad[2];
-    uint32_t class_count[32];  // split pipeline: items per shape class (provider x position of the head in its round)
-    uint32_t class_cursor[32];
+    // device-only tail (the host reads the struct up to here)
+    uint32_t class_count[SSE_N_BUCKETS];  // split pipeline: items per bucket (see item_bucket)
+    uint32_t class_cursor[SSE_N_BUCKETS];
 };
 
 struct KParams {

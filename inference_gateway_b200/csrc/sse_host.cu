@@ -7,6 +7,7 @@
 // (carry, finished flag) -- the per-connection FIFO of provider.go:307-340; H2D of batch k+1 and D2H of
 // batch k overlap kernel k on their own streams.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -121,7 +122,7 @@ int do_launch(sse_ctx *c, Slot &s, uint32_t n_segs, cudaStream_t st) {
         else {   // default: split pipeline produce -> decode -> finalize
             e = sse_launch_produce_kernel(p, (void *)st, c->sm_count);
             if (e == 0) e = sse_launch_decode_finalize(p, (void *)st, c->sm_count, c->device);
-            c->launches += (c->cfg.flags & SSE_FLAG_CHAINS) ? 5 : 3;
+            c->launches += 6;   // produce, bucket hist/scan/scatter, decode, finalize
         }
         if (e != 0) { cu_ok((cudaError_t)e, "stream kernel launch"); return SSE_ERR_CUDA; }
     }
@@ -130,7 +131,7 @@ int do_launch(sse_ctx *c, Slot &s, uint32_t n_segs, cudaStream_t st) {
 }
 
 int do_download(sse_ctx *c, Slot &s, sse_result *res, cudaStream_t st) {
-    CU(cudaMemcpyAsync(s.h_ctr, s.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s.h_ctr, s.d_ctr, offsetof(Counters, class_count), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     const Counters k = *s.h_ctr;
     memset(res, 0, sizeof *res);

@@ -316,7 +316,6 @@ sse_stream_kernel(const KParams P) {
                                 const uint32_t cls = ((ord == 1u ? 0u : (ord == 0u ? 1u : ord)) << 2) | (seg.provider & 3u);
                                 it.y = (uint32_t)(e.pay_e - e.pay_s) | (cls << 24) | ((mode & SSE_MODE_R) ? 0x80000000u : 0u);
                                 it.w = s;
-                                if (P.flags & SSE_FLAG_CHAINS) atomicAdd(&P.ctr->class_count[cls], 1u);
                                 P.items[qb + e.rel] = it;
                                 if (P.flags & SSE_FLAG_CHAINS) P.item_deps[qb + e.rel] = make_uint2(db + e.dfirst, e.ndeps);
                             } else {

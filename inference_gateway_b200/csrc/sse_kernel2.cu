@@ -861,8 +861,8 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
         if (base >= n_items) break;
         const uint32_t idx = base + lane;
         if (idx < n_items) {
-            const bool sorted = (P.flags & SSE_FLAG_CHAINS) != 0;
-            const uint4 it = sorted ? P.items_sorted[idx] : P.items[idx];
+            const bool sorted = chains;
+            const uint4 it = P.items_sorted[idx];
             L.p = it.x; L.plen = it.y & 0x00FFFFFFu; L.pe = it.x + L.plen; L.rec = it.z; L.slot = it.w;   // slot: segment index
             L.frame = P.recs[it.z].frame;
             L.dep_first = L.dep_cnt = 0;
@@ -938,23 +938,77 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
 }
 
 
-// ---------------------------------------------------------------- split pipeline, stage 1b: group items by shape class
-// (counting sort, 32 classes: provider x position of the line among its round's decoded lines). Lanes of a decode batch then
-// walk lines of the same shape and share the divergent parts of the automaton.
-__global__ void sse_class_scan_kernel(const KParams P) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        uint32_t run = 0;
-        for (int c = 0; c < 32; c++) { P.ctr->class_cursor[c] = run; run += P.ctr->class_count[c]; }
-    }
+// ---------------------------------------------------------------- split pipeline, stage 1b: order the work items
+// A decode warp takes 32 items and runs until the longest of them is done, so a batch of mixed lengths idles most lanes
+// (payloads are lognormal 96..4096 B: in arrival order a batch is 34 % busy). Counting sort by payload length / 64, longest
+// bucket first: batches are then 94 % busy and the long lines do not land on the tail of the kernel. With SSE_FLAG_CHAINS the
+// key is the shape class instead (provider x position of the line in its round), which the chain templates need.
+constexpr int N_BUCKETS = SSE_N_BUCKETS;
+__device__ __forceinline__ uint32_t item_bucket(const KParams &P, uint32_t y) {
+    const uint32_t cls = (y >> 24) & 31u;
+    if (P.flags & SSE_FLAG_CHAINS) return cls;
+    return (((uint32_t)SSE_LEN_BUCKETS - 1u - min((y & 0x00FFFFFFu) >> SSE_LEN_SHIFT, (uint32_t)SSE_LEN_BUCKETS - 1u)) << 5) | cls;
 }
-__global__ void sse_class_scatter_kernel(const KParams P) {
+__global__ void sse_bucket_hist_kernel(const KParams P) {
+    __shared__ uint32_t h[N_BUCKETS];
+    for (int b = threadIdx.x; b < N_BUCKETS; b += blockDim.x) h[b] = 0;
+    __syncthreads();
     const uint32_t n = min(P.ctr->n_items, P.cap_items);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint4 it = P.items[i];
-        const uint32_t cls = (it.y >> 24) & 31u;
-        const uint32_t pos = atomicAdd(&P.ctr->class_cursor[cls], 1u);
-        P.items_sorted[pos] = it;
-        P.item_deps_sorted[pos] = P.item_deps[i];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&h[item_bucket(P, P.items[i].y)], 1u);
+    __syncthreads();
+    for (int b = threadIdx.x; b < N_BUCKETS; b += blockDim.x) if (h[b]) atomicAdd(&P.ctr->class_count[b], h[b]);
+}
+constexpr int SCAN_TPB = 1024, SCAN_PER = N_BUCKETS / SCAN_TPB;
+static_assert(N_BUCKETS % SCAN_TPB == 0, "bucket count");
+__global__ void __launch_bounds__(SCAN_TPB) sse_bucket_scan_kernel(const KParams P) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t t = threadIdx.x, lane = t & 31u;
+    uint32_t c[SCAN_PER], mine = 0;
+    #pragma unroll
+    for (int k = 0; k < SCAN_PER; k++) { c[k] = P.ctr->class_count[t * SCAN_PER + k]; mine += c[k]; }
+    uint32_t incl = mine;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, d); if ((int)lane >= d) incl += v; }
+    if (lane == 31) wsum[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        const uint32_t w = wsum[t];
+        uint32_t wi = w;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, wi, d); if ((int)lane >= d) wi += v; }
+        wsum[t] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = wsum[t >> 5] + incl - mine;
+    #pragma unroll
+    for (int k = 0; k < SCAN_PER; k++) { P.ctr->class_cursor[t * SCAN_PER + k] = run; run += c[k]; }
+}
+constexpr int SCATTER_TPB = 256, SCATTER_IPT = 8;   // one block places 2048 consecutive items
+__global__ void __launch_bounds__(SCATTER_TPB) sse_bucket_scatter_kernel(const KParams P) {
+    __shared__ uint32_t h[N_BUCKETS], base[N_BUCKETS];
+    const uint32_t n = min(P.ctr->n_items, P.cap_items);
+    const bool chains = (P.flags & SSE_FLAG_CHAINS) != 0;
+    for (uint32_t blk = blockIdx.x * (SCATTER_TPB * SCATTER_IPT); blk < n; blk += gridDim.x * (SCATTER_TPB * SCATTER_IPT)) {
+        for (int b = threadIdx.x; b < N_BUCKETS; b += SCATTER_TPB) h[b] = 0;
+        __syncthreads();
+        uint4 it[SCATTER_IPT]; uint32_t rank[SCATTER_IPT];
+        #pragma unroll
+        for (int k = 0; k < SCATTER_IPT; k++) {
+            const uint32_t i = blk + k * SCATTER_TPB + threadIdx.x;
+            if (i < n) { it[k] = P.items[i]; rank[k] = atomicAdd(&h[item_bucket(P, it[k].y)], 1u); }
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < N_BUCKETS; b += SCATTER_TPB) if (h[b]) base[b] = atomicAdd(&P.ctr->class_cursor[b], h[b]);
+        __syncthreads();
+        #pragma unroll
+        for (int k = 0; k < SCATTER_IPT; k++) {
+            const uint32_t i = blk + k * SCATTER_TPB + threadIdx.x;
+            if (i < n) {
+                const uint32_t pos = base[item_bucket(P, it[k].y)] + rank[k];
+                P.items_sorted[pos] = it[k];
+                if (chains) P.item_deps_sorted[pos] = P.item_deps[i];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -1030,10 +1084,9 @@ int sse_launch_stream_kernel_v2(const KParams &p, void *stream, int sm_count, in
 }
 
 int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int device) {
-    if (p.flags & SSE_FLAG_CHAINS) {
-        sse_class_scan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
-        sse_class_scatter_kernel<<<sm_count * 4, 256, 0, (cudaStream_t)stream>>>(p);
-    }
+    sse_bucket_hist_kernel<<<sm_count * 2, 512, 0, (cudaStream_t)stream>>>(p);
+    sse_bucket_scan_kernel<<<1, SCAN_TPB, 0, (cudaStream_t)stream>>>(p);
+    sse_bucket_scatter_kernel<<<sm_count * 2, SCATTER_TPB, 0, (cudaStream_t)stream>>>(p);
     sse_decode_kernel<<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
