@@ -26,7 +26,7 @@ constexpr int V2_BUF = 6144;       // line window per warp
 constexpr int RING = 128;          // work items per warp
 constexpr int SEGSLOTS = 8;        // segments in flight per warp
 #ifndef SSE_ROUNDS
-#define SSE_ROUNDS 8
+#define SSE_ROUNDS 4
 #endif
 #ifndef SSE_KSTEPS
 #define SSE_KSTEPS 2
@@ -916,23 +916,23 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
                         }
                     }
                 }
-                // strings that need unquoting were queued by the lanes: decode them with the whole warp
-                __syncwarp();
-                unsigned jm = __ballot_sync(FULL, J->n > 0);
-                while (jm) {
-                    const int leader = __ffs(jm) - 1;
-                    jm &= jm - 1;
-                    LaneJobs &LJ = Jw[leader];
-                    const uint32_t nj = LJ.n;
-                    for (uint32_t k = 0; k < nj; k++) {
-                        const UnquoteJob jb = LJ.j[k];
-                        warp_unquote(P.out, jb.s, jb.e, P.text + jb.dst, jb.patch);
-                    }
-                    __syncwarp();
-                    if ((int)lane == leader) LJ.n = 0;
+            }
+            // strings that need unquoting were queued by the lanes: decode them with the whole warp
+            __syncwarp();
+            unsigned jm = __ballot_sync(FULL, J->n > 0);
+            while (jm) {
+                const int leader = __ffs(jm) - 1;
+                jm &= jm - 1;
+                LaneJobs &LJ = Jw[leader];
+                const uint32_t nj = LJ.n;
+                for (uint32_t k = 0; k < nj; k++) {
+                    const UnquoteJob jb = LJ.j[k];
+                    warp_unquote(P.out, jb.s, jb.e, P.text + jb.dst, jb.patch);
                 }
                 __syncwarp();
+                if ((int)lane == leader) LJ.n = 0;
             }
+            __syncwarp();
         }
     }
 }
