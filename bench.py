@@ -218,6 +218,15 @@ def main():
     valid_frames = int(res.segs["frame_count"].astype(np.int64).sum()) + sum(
         int(res.runs["frame_count"][j]) for j in range(int(res.raw.n_runs)))
     counts["frames"] = valid_frames        # frames of lines after a terminating chunk are allocated but cut from the result
+    # bytes of the delivered frames (b_out of SURVEY 8(d)), wherever they live: materialised in the out arena or spans of the input
+    cs = np.concatenate([[0], np.cumsum(res.frames["len"].astype(np.int64))])
+    ff, fc = res.segs["frame_first"].astype(np.int64), res.segs["frame_count"].astype(np.int64)
+    frame_bytes = int((cs[ff + fc] - cs[ff]).sum())
+    for j in range(int(res.raw.n_runs)):
+        a, b = int(res.runs["frame_first"][j]), int(res.runs["frame_count"][j])
+        frame_bytes += int(cs[a + b] - cs[a])
+    counts["frame_bytes"] = frame_bytes
+    counts["zero_copy_frames"] = int(np.count_nonzero(res.frames["off"] >= res.in_base))
     terminated = int(np.count_nonzero(res.segs["flags"] & 1))
     ok_recs = int(np.count_nonzero(res.recs["flags"] & 1))
 
@@ -302,8 +311,12 @@ def main():
     value = chunks_per_step * args.steps / (dev_ms / 1e3)
 
     # ---- roofline of the stream kernel (rank 0's launch): algorithmic bytes / measured duration
-    alg_bytes = (counts["in_bytes"] + counts["out_bytes"] + 8 * counts["frames"] + 32 * counts["recs"] + 48 * counts["tcs"]
-                 + 24 * counts["usages"] + counts["text_bytes"] + (16 + 32 + 16) * n_segs)
+    # b_in read once + b_out delivered once + frame table + records (+ per-segment descriptors and state).
+    # moved_bytes is what the zero-copy path really has to touch: frames that are spans of the input are never written.
+    side = (8 * counts["frames"] + 32 * counts["recs"] + 48 * counts["tcs"] + 24 * counts["usages"] + counts["text_bytes"]
+            + (16 + 32 + 16) * n_segs)
+    alg_bytes = counts["in_bytes"] + counts["frame_bytes"] + side
+    moved_bytes = counts["in_bytes"] + counts["out_bytes"] + side
     kern_s = (dev_ms / 1e3) / args.steps
     peak, peak_src = 6650.0, "fallback"
     try:
@@ -321,8 +334,9 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": "split pipeline: sse_stream_kernel<produce> + sse_decode_kernel + sse_finalize_kernel (whole step)",
-                "alg_bytes_per_launch": alg_bytes, "kernel_ms": 1e3 * kern_s,
+                "kernel": "split pipeline: sse_stream_kernel<produce> + bucket sort (3 small kernels) + sse_decode_kernel + sse_finalize_kernel (whole step)",
+                "alg_bytes_per_launch": alg_bytes, "moved_bytes_per_launch": moved_bytes,
+                "zero_copy_frames": counts["zero_copy_frames"], "kernel_ms": 1e3 * kern_s,
                 "hbm_read_frac": counts["in_bytes"] / kern_s / 1e9 / peak}
 
     line = {
@@ -335,7 +349,7 @@ def main():
                    "sse_events_per_step": tot["events"], "chunks_emitted_per_step": tot["frames"],
                    "records_decoded_per_step": tot["recs"], "mean_event_bytes": tot["in_bytes"] / max(1, tot["events"]),
                    "input_bytes_per_step": tot["in_bytes"], "sharding": "hash(conn_id) % n_gpus, no collective",
-                   "l2": "working set (input + output > 500 MB per GPU) exceeds the 126 MB L2; no explicit flush",
+                   "l2": "working set (input + result tables > 350 MB per GPU) exceeds the 126 MB L2; no explicit flush",
                    "streams_terminated": terminated, "records_json_ok": ok_recs},
         "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
     }

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SSE_ABI_VERSION 1
+#define SSE_ABI_VERSION 2
 
 typedef enum {
     SSE_OK = 0,
@@ -71,6 +71,10 @@ typedef struct {
 #define SSE_FLAG_CHAINS 4u     /* split pipeline, experimental: derive the record of a line that differs from the previous decoded
                                   line only by plain bytes inside the content string, and group decode work by line shape */
 #define SSE_FLAG_KERNEL_V2 2u  /* fused producer/consumer kernel (table-driven automaton); default is the split pipeline */
+#define SSE_FLAG_COPY_OUT 8u   /* materialise every frame in the out arena. Default: a frame whose bytes already stand in the
+                                  caller's input arena exactly as the reference would send them (every mode P line, and a mode R
+                                  "data: ...\n" line followed by a blank line) is returned as a span of the input arena and is
+                                  neither copied on the device nor sent back over PCIe (see sse_at) */
 
 /* One segment = the bytes read from ONE connection since the previous batch. in_off is 16-byte aligned. */
 typedef struct {
@@ -82,7 +86,9 @@ typedef struct {
     uint16_t reserved;
 } sse_seg;
 
-/* An emitted frame: one element of the reference's chan []byte. */
+/* An emitted frame: one element of the reference's chan []byte. `off` is an arena offset: below sse_result.in_base it
+ * indexes sse_result.out, at or above it indexes the batch's own input arena (off - in_base); use sse_at(). The same
+ * holds for every span in sse_rec / sse_tc that is not flagged *_TEXT. */
 typedef struct { uint32_t off, len; } sse_frame;
 
 /* sse_rec.flags */
@@ -90,7 +96,7 @@ typedef struct { uint32_t off, len; } sse_frame;
 #define SSE_F_HAS_USAGE      0x0002u /* resp.Usage != nil */
 #define SSE_F_TC_NONNIL      0x0004u /* choices[0].delta.tool_calls != nil */
 #define SSE_F_TC_VALID       0x0008u /* agent.go:224-233 predicate true for some element */
-#define SSE_F_CONTENT_TEXT   0x0010u /* content span is in the text arena (needed unescaping), else out arena */
+#define SSE_F_CONTENT_TEXT   0x0010u /* content span is in the text arena (needed unescaping), else an arena offset (sse_at) */
 #define SSE_F_DONE_LINE      0x0020u /* mode R: line contained "[DONE]" and was swallowed (agent.go:181-184) */
 #define SSE_F_DONE_EXACT     0x0040u /* ... and its payload is exactly "[DONE]" (agent.go:394-396 break) */
 #define SSE_F_TERMINATES     0x0080u /* mode R: finish_reason stop/tool_calls on an emitted chunk (agent.go:235-242) */
@@ -120,7 +126,7 @@ typedef struct {
 #define SSE_TC_HAS_ID    0x01u
 #define SSE_TC_HAS_TYPE  0x02u
 #define SSE_TC_HAS_FUNC  0x04u
-#define SSE_TC_ID_TEXT   0x10u   /* span is in the text arena (else out arena) */
+#define SSE_TC_ID_TEXT   0x10u   /* span is in the text arena (else an arena offset, sse_at) */
 #define SSE_TC_TYPE_TEXT 0x20u
 #define SSE_TC_NAME_TEXT 0x40u
 #define SSE_TC_ARGS_TEXT 0x80u
@@ -160,7 +166,7 @@ typedef struct {
     int32_t  status;       /* SSE_OK or SSE_ERR_OVERFLOW */
     uint32_t n_segs, n_frames, n_recs, n_tcs, n_usages, n_runs;
     uint32_t out_bytes, text_bytes;
-    const uint8_t        *out;      /* emitted bytes (frames index into this) */
+    const uint8_t        *out;      /* emitted bytes that had to be materialised (reframed, carried over or assembled lines) */
     const sse_frame      *frames;
     const sse_rec        *recs;
     const sse_tc         *tcs;
@@ -170,7 +176,13 @@ typedef struct {
     const sse_seg_result *segs;
     uint32_t n_decoded, n_derived;  /* statistics: lines decoded by the automaton / derived from the previous line's parse */
     uint32_t overflow;              /* SSE_OVF_* bits when status == SSE_ERR_OVERFLOW: which sse_config capacity to raise */
+    uint32_t in_base;               /* arena offsets >= in_base refer to in[off - in_base] */
+    const uint8_t *in;              /* the batch's input arena (sse_batch.in_arena), lent until sse_release like out */
 } sse_result;
+
+/* Resolve an arena offset (frame.off, content_off, tool-call spans without the *_TEXT flag):
+ * off >= r->in_base ? r->in + (off - r->in_base) : r->out + off. */
+const uint8_t *sse_at(const sse_result *r, uint32_t off);
 
 #define SSE_OVF_OUT    0x01u  /* out_arena_bytes / max_frames / max_recs (bump-allocated together per round) */
 #define SSE_OVF_TCS    0x02u  /* max_tcs */

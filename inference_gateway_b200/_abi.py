@@ -8,6 +8,7 @@ from . import build as _build
 
 SSE_OK, SSE_ERR_NO_DEVICE, SSE_ERR_CUDA, SSE_ERR_ARG, SSE_ERR_BUSY, SSE_ERR_OVERFLOW, SSE_ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
 MODE_P, MODE_R, MODE_PARSE = 0, 1, 2
+FLAG_KERNEL_V1, FLAG_KERNEL_V2, FLAG_CHAINS, FLAG_COPY_OUT = 1, 2, 4, 8
 NONE = 0xFFFFFFFF
 
 F_JSON_OK, F_HAS_USAGE, F_TC_NONNIL, F_TC_VALID, F_CONTENT_TEXT = 0x1, 0x2, 0x4, 0x8, 0x10
@@ -65,7 +66,8 @@ class Result(C.Structure):
                 ("out", C.POINTER(C.c_uint8)), ("frames", C.POINTER(Frame)), ("recs", C.POINTER(Rec)),
                 ("tcs", C.POINTER(Tc)), ("usages", C.POINTER(Usage)), ("text", C.POINTER(C.c_uint8)),
                 ("runs", C.POINTER(Run)), ("segs", C.POINTER(SegResult)),
-                ("n_decoded", C.c_uint32), ("n_derived", C.c_uint32), ("overflow", C.c_uint32)]
+                ("n_decoded", C.c_uint32), ("n_derived", C.c_uint32), ("overflow", C.c_uint32),
+                ("in_base", C.c_uint32), ("in_", C.POINTER(C.c_uint8))]
 
 
 class Batch(C.Structure):
@@ -86,7 +88,7 @@ assert C.sizeof(Seg) == 16 and C.sizeof(Rec) == 32 and C.sizeof(Tc) == 48 and C.
 EXPORTS = [
     "sse_init", "sse_destroy", "sse_strerror", "sse_last_cuda_error", "sse_abi_version", "sse_default_config",
     "sse_acquire", "sse_submit", "sse_collect", "sse_release", "sse_reset_conn", "sse_reset_all",
-    "sse_upload", "sse_launch", "sse_download", "sse_launch_count",
+    "sse_upload", "sse_launch", "sse_download", "sse_launch_count", "sse_at",
     "sse_agent_new", "sse_agent_free", "sse_agent_reset", "sse_agent_feed", "sse_agent_content",
     "sse_agent_has_tool_calls", "sse_agent_terminated", "sse_agent_tool_calls",
     "sse_telemetry_new", "sse_telemetry_free", "sse_telemetry_reset", "sse_telemetry_feed", "sse_telemetry_finish",
@@ -129,6 +131,8 @@ def load(build_if_missing: bool = True):
     L.sse_launch.argtypes = [vp, i32, u32, vp]
     L.sse_download.argtypes = [vp, i32, C.POINTER(Result), vp]
     L.sse_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.sse_at.argtypes = [C.POINTER(Result), u32]
+    L.sse_at.restype = C.POINTER(C.c_uint8)
     L.sse_agent_new.restype = vp
     L.sse_agent_free.argtypes = [vp]
     L.sse_agent_free.restype = None

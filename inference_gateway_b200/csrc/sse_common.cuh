@@ -81,6 +81,7 @@ struct LineEnt {
     uint16_t dfirst;    // head: index of its first dependent among this round's dependents
     uint16_t ndeps;     // head: number of dependents that follow it
     uint16_t chain;     // 0 head, 1 dependent
+    uint16_t zc;        // 1: the frame's bytes stand in the input arena as they are (no copy; offsets are input offsets)
 };
 enum : uint8_t { K_DROP = 0, K_EMIT = 1, K_DONE = 2, K_DONE_EXACT = 3 };
 

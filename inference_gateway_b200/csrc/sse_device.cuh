@@ -56,6 +56,7 @@ struct KParams {
     uint32_t carry_slot;
     // results
     uint8_t *out;            uint32_t cap_out;
+    uint32_t in_base;        // in == out + in_base: arena offsets >= in_base are input bytes (zero-copy frames)
     sse_frame *frames;       uint32_t cap_frames;
     sse_rec *recs;           uint32_t cap_recs;
     sse_tc *tcs;             uint32_t cap_tcs;

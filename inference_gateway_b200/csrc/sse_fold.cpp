@@ -34,7 +34,7 @@ struct AccMap {
 
 inline sse_bytes span(const sse_result *r, uint32_t off, uint32_t len, bool text) {
     sse_bytes b;
-    b.p = (text ? r->text : r->out) + off;
+    b.p = text ? r->text + off : sse_at(r, off);
     b.n = len;
     return b;
 }
@@ -243,7 +243,7 @@ int sse_telemetry_feed(sse_telemetry_fold *f, const sse_result *res, uint32_t se
             const sse_rec *rec = nullptr;
             while (ri < run.rec_count && (res->recs[run.rec_first + ri].frame == SSE_NONE || res->recs[run.rec_first + ri].frame < fi)) ri++;
             if (ri < run.rec_count && res->recs[run.rec_first + ri].frame == fi) rec = &res->recs[run.rec_first + ri];
-            const uint8_t *b = res->out + fr.off;
+            const uint8_t *b = sse_at(res, fr.off);
             if (fr.len >= 2 && b[fr.len - 1] == '\n' && b[fr.len - 2] == '\n' && rec && !(fr.len >= 1 && b[0] == '\n')) {
                 // a reframed "data: X\n\n" frame (mode R): the line and its separator in one element
                 tele_line(f, res, fr.len - 1, rec);

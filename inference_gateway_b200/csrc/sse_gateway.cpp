@@ -129,7 +129,7 @@ int ssegw_pump(ssegw *g) {
             const sse_run *run = &res.segs[k].run;
             for (;;) {
                 for (uint32_t f = run->frame_first; f < run->frame_first + run->frame_count; f++) {
-                    s.chan.emplace_back((const char *)res.out + res.frames[f].off, res.frames[f].len);   // fresh copy per element
+                    s.chan.emplace_back((const char *)sse_at(&res, res.frames[f].off), res.frames[f].len);   // fresh copy per element
                     delivered++;
                 }
                 if (run->next == SSE_NONE) break;

@@ -49,6 +49,10 @@ struct Slot {
 
 } // namespace
 
+// Device layout of a slot's byte arenas: [out arena | pad | in arena] in ONE allocation, so that a single base pointer and
+// a 32-bit offset address both. Offsets >= in_base are input bytes (zero-copy frames and their spans).
+static inline uint32_t in_base_of(const sse_config &cfg) { return (cfg.out_arena_bytes + 255u) & ~255u; }
+
 struct sse_ctx {
     int device = 0;
     int sm_count = 0;
@@ -73,7 +77,8 @@ void free_slot(Slot &s) {
     cudaFreeHost(s.h_in); cudaFreeHost(s.h_segs); cudaFreeHost(s.h_out); cudaFreeHost(s.h_frames); cudaFreeHost(s.h_recs);
     cudaFreeHost(s.h_tcs); cudaFreeHost(s.h_usages); cudaFreeHost(s.h_text); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_segres);
     cudaFreeHost(s.h_ctr);
-    cudaFree(s.d_in); cudaFree(s.d_segs); cudaFree(s.d_out); cudaFree(s.d_frames); cudaFree(s.d_recs); cudaFree(s.d_tcs);
+    cudaFree(s.d_segs); cudaFree(s.d_out);   // d_in lives inside d_out's allocation
+    cudaFree(s.d_frames); cudaFree(s.d_recs); cudaFree(s.d_tcs);
     cudaFree(s.d_usages); cudaFree(s.d_text); cudaFree(s.d_runs); cudaFree(s.d_segres); cudaFree(s.d_ctr); cudaFree(s.d_items); cudaFree(s.d_segterm); cudaFree(s.d_itemdeps); cudaFree(s.d_deps); cudaFree(s.d_items2); cudaFree(s.d_itemdeps2);
 }
 
@@ -81,7 +86,7 @@ KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
     KParams p{};
     p.in = s.d_in; p.segs = s.d_segs; p.n_segs = n_segs; p.max_conns = c->cfg.max_conns;
     p.conns = c->d_conns; p.carry = c->d_carry; p.carry_slot = c->cfg.carry_slot_bytes;
-    p.out = s.d_out; p.cap_out = c->cfg.out_arena_bytes;
+    p.out = s.d_out; p.cap_out = c->cfg.out_arena_bytes; p.in_base = in_base_of(c->cfg);
     p.frames = s.d_frames; p.cap_frames = c->cfg.max_frames;
     p.recs = s.d_recs; p.cap_recs = c->cfg.max_recs;
     p.tcs = s.d_tcs; p.cap_tcs = c->cfg.max_tcs;
@@ -155,7 +160,7 @@ int do_download(sse_ctx *c, Slot &s, sse_result *res, cudaStream_t st) {
     CU(cudaStreamSynchronize(st));
     res->out = s.h_out; res->frames = s.h_frames; res->recs = s.h_recs; res->tcs = s.h_tcs; res->usages = s.h_usages;
     res->text = s.h_text; res->runs = s.h_runs; res->segs = s.h_segres;
-    (void)c;
+    res->in = s.h_in; res->in_base = in_base_of(c->cfg);
     return SSE_OK;
 }
 
@@ -164,6 +169,8 @@ int do_download(sse_ctx *c, Slot &s, sse_result *res, cudaStream_t st) {
 extern "C" {
 
 int sse_abi_version(void) { return SSE_ABI_VERSION; }
+
+const uint8_t *sse_at(const sse_result *r, uint32_t off) { return off >= r->in_base ? r->in + (off - r->in_base) : r->out + off; }
 
 const char *sse_last_cuda_error(void) { return g_cuda_err; }
 
@@ -203,6 +210,7 @@ int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
     if (!cfg || !out || cfg->struct_size != sizeof(sse_config)) return SSE_ERR_ARG;
     if (cfg->n_slots < 1 || cfg->n_slots > 8 || cfg->max_conns == 0 || cfg->max_segs == 0 ||
         (cfg->in_arena_bytes & 15u) || cfg->carry_slot_bytes < 8192 + 16) return SSE_ERR_ARG;
+    if ((uint64_t)in_base_of(*cfg) + cfg->in_arena_bytes + 16 >= (1ull << 31)) return SSE_ERR_ARG;   // arena offsets are 31-bit
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) {
         cu_ok(cudaGetLastError(), "cudaGetDeviceCount");
@@ -234,8 +242,10 @@ int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
         ok = ok && halloc(s.h_out, cfg->out_arena_bytes) && halloc(s.h_frames, cfg->max_frames) && halloc(s.h_recs, cfg->max_recs);
         ok = ok && halloc(s.h_tcs, cfg->max_tcs) && halloc(s.h_usages, cfg->max_usages) && halloc(s.h_text, cfg->text_arena_bytes);
         ok = ok && halloc(s.h_runs, cfg->max_runs) && halloc(s.h_segres, cfg->max_segs) && halloc(s.h_ctr, 1);
-        ok = ok && dalloc(s.d_in, (size_t)cfg->in_arena_bytes + 16) && dalloc(s.d_segs, cfg->max_segs);
-        ok = ok && dalloc(s.d_out, cfg->out_arena_bytes) && dalloc(s.d_frames, cfg->max_frames) && dalloc(s.d_recs, cfg->max_recs);
+        ok = ok && dalloc(s.d_segs, cfg->max_segs);
+        ok = ok && dalloc(s.d_out, (size_t)in_base_of(*cfg) + cfg->in_arena_bytes + 16);
+        if (ok) s.d_in = s.d_out + in_base_of(*cfg);
+        ok = ok && dalloc(s.d_frames, cfg->max_frames) && dalloc(s.d_recs, cfg->max_recs);
         ok = ok && dalloc(s.d_tcs, cfg->max_tcs) && dalloc(s.d_usages, cfg->max_usages) && dalloc(s.d_text, cfg->text_arena_bytes);
         ok = ok && dalloc(s.d_runs, cfg->max_runs) && dalloc(s.d_segres, cfg->max_segs) && dalloc(s.d_ctr, 1);
         ok = ok && dalloc(s.d_items, cfg->max_recs) && dalloc(s.d_segterm, cfg->max_segs);

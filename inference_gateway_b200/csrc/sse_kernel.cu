@@ -66,11 +66,13 @@ sse_stream_kernel(const KParams P) {
         bool in_long = (cst.flags & CONN_LONG) != 0;
         int clen = (int)cst.carry_len;     // bytes in the carry slot
         int pend = 0;                      // bytes at the window front (end at a 16-aligned offset)
+        bool carry_front = false;          // the window front holds bytes of an earlier batch (not in this input arena)
         if (!in_long && clen > 0) {
             int A = (clen + 15) & ~15;
             copy_g2s_bytes(buf + (A - clen), slot, clen);
-            pend = clen; clen = 0;
+            pend = clen; clen = 0; carry_front = true;
         }
+        const bool zero_copy = !(P.flags & SSE_FLAG_COPY_OUT);
         int consumed = 0;
         const int in_len = (int)seg.in_len;
         const uint8_t *src = P.in + seg.in_off;
@@ -89,6 +91,10 @@ sse_stream_kernel(const KParams P) {
             }
             consumed += nload;
             const int fill = A + nload;
+            // window position w >= zc_lo holds input byte seg.in_off + ... = w + in_delta (a tail moved to the front is input too)
+            const int in_delta = (int)seg.in_off + (consumed - nload) - A;
+            const int zc_lo = carry_front ? A : base;
+            carry_front = false;
             __syncwarp();
             int pos = base;
 
@@ -163,7 +169,7 @@ sse_stream_kernel(const KParams P) {
                 const int n_done = min((int)W.done_cnt, DONE_MAX);
 
                 // classify: one lane per line (2 passes for 64 lines)
-                uint32_t my_flen[2] = { 0, 0 }, my_kind[2] = { 0, 0 }, my_parse[2] = { 0, 0 };
+                uint32_t my_flen[2] = { 0, 0 }, my_kind[2] = { 0, 0 }, my_parse[2] = { 0, 0 }, my_zc[2] = { 0, 0 };
                 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     int i = (int)lane + 32 * h;
@@ -171,7 +177,7 @@ sse_stream_kernel(const KParams P) {
                         int ls = (i == 0) ? pos : (int)W.lt[i - 1].nl + 1;
                         int nl = W.lt[i].nl;
                         int a = ls, b = nl + 1;
-                        uint32_t kind, parse = 0; int src_s = ls, pay_s = ls, pay_e = ls, flen = 0;
+                        uint32_t kind, parse = 0, zc = 0; int src_s = ls, pay_s = ls, pay_e = ls, flen = 0;
                         if (mode & SSE_MODE_R) {
                             trim_space(buf, a, b);                          // agent.go:178-179
                             bool has_done = false;                          // agent.go:181
@@ -185,22 +191,26 @@ sse_stream_kernel(const KParams P) {
                                 kind = exact ? K_DONE_EXACT : K_DONE; parse = 1;
                             } else if (pref && b - a > 6) {                  // agent.go:190-197
                                 kind = K_EMIT; src_s = a; pay_s = a + 6; pay_e = b; flen = (b - a) + 2; parse = 1;
+                                // "data: " + payload + "\n\n" is already what the input holds when nothing was trimmed
+                                // at the end and the separator line is empty (the usual upstream framing)
+                                zc = (zero_copy && b == nl && a >= zc_lo && nl + 1 < fill && buf[nl + 1] == '\n') ? 1u : 0u;
                             } else kind = K_DROP;
                         } else {
                             kind = K_EMIT; src_s = ls; flen = nl + 1 - ls;   // routes.go:613 verbatim
+                            zc = (zero_copy && ls >= zc_lo) ? 1u : 0u;
                             if ((mode & SSE_MODE_PARSE) && is_data_prefix(buf + ls, nl + 1 - ls)) { parse = 1; pay_s = ls + 6; pay_e = nl; }
                         }
                         LineEnt &e = W.lt[i];
                         e.src_s = (uint16_t)src_s; e.pay_s = (uint16_t)pay_s; e.pay_e = (uint16_t)pay_e;
-                        e.flen = (uint16_t)flen; e.kind = (uint8_t)kind; e.parse = (uint8_t)parse;
-                        my_flen[h] = (uint32_t)flen; my_kind[h] = kind; my_parse[h] = parse;
+                        e.flen = (uint16_t)flen; e.kind = (uint8_t)kind; e.parse = (uint8_t)parse; e.zc = (uint16_t)zc;
+                        my_flen[h] = (uint32_t)flen; my_kind[h] = kind; my_parse[h] = parse; my_zc[h] = zc;
                     }
                 }
                 // allocate: exclusive prefix (line order) of frame bytes / frame count / rec count
                 uint32_t pre_b[2], pre_f[2], pre_r[2], tot_b = 0, tot_f = 0, tot_r = 0;
                 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    uint32_t vb = my_flen[h], vf = my_flen[h] ? 1u : 0u, vr = my_parse[h];
+                    uint32_t vb = my_zc[h] ? 0u : my_flen[h], vf = my_flen[h] ? 1u : 0u, vr = my_parse[h];
                     uint32_t sb = vb, sf = vf, sr = vr;
                     #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
@@ -274,14 +284,18 @@ sse_stream_kernel(const KParams P) {
                 // frame table
                 #pragma unroll
                 for (int h = 0; h < 2; h++)
-                    if (my_flen[h]) { sse_frame f; f.off = ob + pre_b[h]; f.len = my_flen[h]; P.frames[fb + pre_f[h]] = f; }
+                    if (my_flen[h]) {
+                        sse_frame f; f.len = my_flen[h];
+                        f.off = my_zc[h] ? P.in_base + (uint32_t)(in_delta + (int)W.lt[(int)lane + 32 * h].src_s) : ob + pre_b[h];
+                        P.frames[fb + pre_f[h]] = f;
+                    }
                 __syncwarp();
                 // emit: warp-cooperative serializer, frames back to back in line order
                 {
                     uint32_t o = ob;
                     for (int i = 0; i < n_lines; i++) {
                         const LineEnt e = W.lt[i];
-                        if (!e.flen) continue;
+                        if (!e.flen || e.zc) continue;
                         uint8_t *dst = P.out + o;
                         const uint8_t *sp = buf + e.src_s;
                         if (mode & SSE_MODE_R) {
@@ -301,14 +315,14 @@ sse_stream_kernel(const KParams P) {
                         const LineEnt e = W.lt[i];
                         ParseCtx cx; cx.sm = buf; cx.P = &P; cx.S = &cs.schema;
                         cx.emitted = my_kind[h] == K_EMIT;
-                        cx.out_delta = (int64_t)(ob + pre_b[h]) - (int64_t)e.src_s;
+                        cx.out_delta = e.zc ? (int64_t)P.in_base + in_delta : (int64_t)(ob + pre_b[h]) - (int64_t)e.src_s;
                         if (SPLIT && my_kind[h] == K_EMIT) {
                             sse_rec stub;
                             stub.frame = fb + pre_f[h]; stub.flags = 0; stub.content_off = stub.content_len = 0; stub.tc_first = SSE_NONE;
                             stub.tc_count = 0; stub.n_choices = 0; stub.usage = SSE_NONE; stub.payload_len = (uint32_t)(e.pay_e - e.pay_s);
                             P.recs[rb + pre_r[h]] = stub;
                             uint4 it;
-                            it.x = ob + pre_b[h] + (uint32_t)(e.pay_s - e.src_s);
+                            it.x = (uint32_t)(cx.out_delta + (int64_t)e.pay_s);
                             it.z = rb + pre_r[h];
                             if (e.chain == 0) {
                                 // shape class; the second decoded line of a round (first content delta, the longest) sorts first: long work early

@@ -51,6 +51,15 @@ class BatchResult:
     text: np.ndarray
     runs: np.ndarray
     segs: np.ndarray
+    in_arena: np.ndarray = None     # the batch's input arena; arena offsets >= in_base index it (zero-copy frames)
+    in_base: int = 0xFFFFFFFF
+
+    def at(self, off: int, length: int) -> bytes:
+        """sse_at(): resolve an arena offset."""
+        if off >= self.in_base:
+            o = off - self.in_base
+            return self.in_arena[o:o + length].tobytes()
+        return self.out[off:off + length].tobytes()
 
     def seg_runs(self, i: int):
         s = self.segs[i]
@@ -64,11 +73,10 @@ class BatchResult:
 
     def seg_frames(self, i: int) -> list:
         out = []
-        ob = self.out
         for ff, fc, _, _ in self.seg_runs(i):
             for k in range(ff, ff + fc):
                 f = self.frames[k]
-                out.append(ob[int(f["off"]):int(f["off"]) + int(f["len"])].tobytes())
+                out.append(self.at(int(f["off"]), int(f["len"])))
         return out
 
     def seg_recs(self, i: int) -> list:
@@ -78,8 +86,7 @@ class BatchResult:
         return out
 
     def span(self, off: int, length: int, in_text: bool) -> bytes:
-        a = self.text if in_text else self.out
-        return a[off:off + length].tobytes()
+        return self.text[off:off + length].tobytes() if in_text else self.at(off, length)
 
 
 class SseEngine:
@@ -141,6 +148,7 @@ class SseEngine:
             _np_view(res.text, res.text_bytes, np.uint8),
             _np_view(C.cast(res.runs, C.POINTER(C.c_uint8)), res.n_runs * 20, np.uint8).view(RUN_DT),
             _np_view(C.cast(res.segs, C.POINTER(C.c_uint8)), res.n_segs * 32, np.uint8).view(SEGRES_DT),
+            _np_view(res.in_, self.cfg.in_arena_bytes, np.uint8), int(res.in_base),
         )
 
     def collect(self, slot) -> BatchResult:

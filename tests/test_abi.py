@@ -27,7 +27,7 @@ def test_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} is declared in include/sse_gpu.h but not exported by libssegpu.so"
     assert set(names) == set(A.EXPORTS)
-    assert L.sse_abi_version() == 1
+    assert L.sse_abi_version() == 2
     gw = declared_functions(GW_HEADER, "ssegw_")
     assert len(gw) >= 12
     for n in gw:

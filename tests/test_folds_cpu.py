@@ -14,7 +14,9 @@ from tests.util import agent_results, telemetry_results
 class FakeResult:
     """Builds an sse_result (one segment) from oracle line views, the way the kernel lays it out."""
 
-    def __init__(self, view: orc.StreamView, mode_r: bool):
+    def __init__(self, view: orc.StreamView, mode_r: bool, in_arena: bool = False):
+        # in_arena: every frame is a span of the input arena (zero-copy frames, offsets >= in_base), none is in out
+        IN_BASE = 4096 if in_arena else 0xFFFFFFFF
         out, text = bytearray(), bytearray(b"\0")
         frames, recs, tcs, usages = [], [], [], []
 
@@ -27,7 +29,7 @@ class FakeResult:
                 break
             fidx = A.NONE
             if emitted:
-                fidx = len(frames); frames.append((len(out), len(l.out))); out.extend(l.out)
+                fidx = len(frames); frames.append(((IN_BASE if in_arena else 0) + len(out), len(l.out))); out.extend(l.out)
             ck = l.chunk
             if l.kind == orc.L_DONE_EXACT:
                 recs.append((A.NONE, A.F_DONE_LINE | A.F_DONE_EXACT, 0, 0, A.NONE, 0, 0, A.NONE, 6))
@@ -79,7 +81,12 @@ class FakeResult:
         ob = (C.c_uint8 * max(1, len(out))).from_buffer_copy(bytes(out) or b"\0")
         tb = (C.c_uint8 * len(text)).from_buffer_copy(bytes(text))
         self.keep += [ob, tb]
-        res.out = C.cast(ob, C.POINTER(C.c_uint8)); res.text = C.cast(tb, C.POINTER(C.c_uint8))
+        res.text = C.cast(tb, C.POINTER(C.c_uint8))
+        res.in_base = IN_BASE
+        if in_arena:
+            res.in_ = C.cast(ob, C.POINTER(C.c_uint8)); res.out_bytes = 0
+        else:
+            res.out = C.cast(ob, C.POINTER(C.c_uint8))
         res.frames = C.cast(arr(A.Frame, frames), C.POINTER(A.Frame))
         res.recs = C.cast(arr(A.Rec, recs), C.POINTER(A.Rec))
         res.tcs = C.cast(arr(A.Tc, [tuple(t) for t in tcs]), C.POINTER(A.Tc))
@@ -106,11 +113,12 @@ def _streams():
     return [b for b, _, _ in streams] + extra
 
 
-def test_agent_fold_matches_oracle():
+@pytest.mark.parametrize("in_arena", [False, True])
+def test_agent_fold_matches_oracle(in_arena):
     L = A.load()
     for body in _streams():
         v = orc.reframe(body)
-        fr = FakeResult(v, True)
+        fr = FakeResult(v, True, in_arena)
         f = L.sse_agent_new()
         A.check(L.sse_agent_feed(f, C.byref(fr.res), 0), "feed")
         content, has, term, fin, calls = agent_results(L, f)
@@ -119,7 +127,8 @@ def test_agent_fold_matches_oracle():
         assert calls == orc.parse_tool_calls(v.builder), body[:80]
 
 
-def test_telemetry_fold_matches_oracle():
+@pytest.mark.parametrize("in_arena", [False, True])
+def test_telemetry_fold_matches_oracle(in_arena):
     L = A.load()
     bodies = _streams() + [b"data: {\"usage\":{\"prompt_tokens\":1,\"completion_tokens\":2,\"total_tokens\":3}}\n\n" + b"data: {\"choices\":[]}\n\n" * k + b"data: [DONE]\n\n"
                            for k in range(5)]
@@ -127,7 +136,7 @@ def test_telemetry_fold_matches_oracle():
                b"event: x\ndata: {\"usage\":{\"prompt_tokens\":4}}\n\n", b"data: {\"usage\":{\"prompt_tokens\":5}}\n"]
     for body in bodies:
         v = orc.passthrough(body, parse=True)
-        fr = FakeResult(v, False)
+        fr = FakeResult(v, False, in_arena)
         f = L.sse_telemetry_new()
         A.check(L.sse_telemetry_feed(f, C.byref(fr.res), 0), "feed")
         rc, usage, calls = telemetry_results(L, f)

@@ -279,3 +279,54 @@ def test_overflow_is_reported_not_hidden():
         eng.release(slot)
     finally:
         eng.close()
+
+
+# ------------------------------------------------------------------ zero-copy frames (arena offsets >= in_base)
+def _one_batch(eng, items):
+    slot, res = eng.process(items)
+    try:
+        offs = [[int(res.frames[k]["off"]) for ff, fc, _, _ in res.seg_runs(i) for k in range(ff, ff + fc)] for i in range(len(items))]
+        frames = [res.seg_frames(i) for i in range(len(items))]
+        return offs, frames, int(res.raw.out_bytes), res.in_base
+    finally:
+        eng.release(slot)
+
+
+def test_zero_copy_frames_are_spans_of_the_input_arena():
+    """Default path: a frame whose bytes already stand in the input arena is returned as a span of it (nothing is written to
+    the out arena, nothing comes back over PCIe); anything that had to be assembled is materialised. SSE_FLAG_COPY_OUT
+    materialises every frame. The bytes are the oracle's either way."""
+    from inference_gateway_b200 import SseEngine
+    ev = b'data: {"choices":[{"index":0,"delta":{"content":"hello"},"finish_reason":null}]}'
+    usual = (ev + b"\n\n") * 7 + b"data: [DONE]\n\n"
+    crlf = (ev + b"\r\n\r\n") * 3                      # reframing changes the bytes: materialised in mode R
+    padded = b"  " + ev + b" \n\n" + ev + b"\n\n"       # first event is trimmed at the end: materialised; second is not
+    nosep = ev + b"\n" + ev + b"\n\n"                   # first line has no blank separator: "\n\n" must be synthesised
+    for flags in (0, A.FLAG_COPY_OUT):
+        eng = SseEngine(device=0, max_conns=16, bytes_per_batch=1 << 20, flags=flags)
+        try:
+            eng.reset_all()
+            offs, frames, out_bytes, in_base = _one_batch(eng, [(0, R, usual), (1, P, usual), (2, R, crlf), (3, P, crlf),
+                                                                (4, R, padded), (5, R, nosep)])
+            for i, (body, mode) in enumerate([(usual, R), (usual, P), (crlf, R), (crlf, P), (padded, R), (nosep, R)]):
+                v = orc.reframe(body) if mode & A.MODE_R else orc.passthrough(body)
+                exp = [l.out for l in v.lines if l.kind == orc.L_EMITTED] if mode & A.MODE_R else [l.out for l in v.lines]
+                assert frames[i] == exp
+            zc = [[o >= in_base for o in oo] for oo in offs]
+            if flags & A.FLAG_COPY_OUT:
+                assert not any(any(z) for z in zc) and out_bytes > 0
+            else:
+                assert all(zc[0]) and all(zc[1]) and all(zc[3])          # usual framing, and every mode P line
+                assert not any(zc[2])                                    # \r\n lines are rewritten by the reframe
+                assert zc[4] == [False, True] and zc[5] == [False, True]
+            # second micro-batch: the first line of each segment continues a held-back tail -> assembled -> materialised
+            eng.reset_all()
+            cut = len(ev) // 2
+            _one_batch(eng, [(0, R, usual[:cut]), (1, P, usual[:cut])])
+            offs, frames, _, in_base = _one_batch(eng, [(0, R, usual[cut:]), (1, P, usual[cut:])])
+            assert frames[0][0] == ev + b"\n\n" and frames[1][0] == ev + b"\n"
+            if not flags:
+                assert offs[0][0] < in_base and offs[1][0] < in_base
+                assert all(o >= in_base for o in offs[0][1:]) and all(o >= in_base for o in offs[1][1:])
+        finally:
+            eng.close()
