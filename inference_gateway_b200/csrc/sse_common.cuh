@@ -100,6 +100,7 @@ struct CtaSmem {
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ void prefetch_l2(const uint8_t *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // 4-bit mask of the bytes of w equal to the byte replicated in pat
 __device__ __forceinline__ uint32_t eqmask4(uint32_t w, uint32_t pat) {

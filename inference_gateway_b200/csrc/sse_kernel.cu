@@ -37,11 +37,20 @@ sse_stream_kernel(const KParams P) {
     uint8_t *buf = W.buf;
     const uint32_t lane = lane_id();
 
+    // tickets are taken one segment ahead: while a segment is processed, the next one's first window is on its way to L2
+    uint32_t s_next = 0;
+    if (lane == 0) s_next = atomicAdd(&P.ctr->ticket, 1u);
+    s_next = __shfl_sync(FULL, s_next, 0);
     for (;;) {
-        uint32_t s = 0;
-        if (lane == 0) s = atomicAdd(&P.ctr->ticket, 1u);
-        s = __shfl_sync(FULL, s, 0);
+        const uint32_t s = s_next;
         if (s >= P.n_segs) break;
+        if (lane == 0) s_next = atomicAdd(&P.ctr->ticket, 1u);
+        s_next = __shfl_sync(FULL, s_next, 0);
+        if (s_next < P.n_segs) {
+            const sse_seg nx = P.segs[s_next];
+            const uint32_t nb = min(nx.in_len, (uint32_t)BUF);
+            for (uint32_t o = lane * 128u; o < nb; o += 32u * 128u) prefetch_l2(P.in + nx.in_off + o);
+        }
 
         const sse_seg seg = P.segs[s];
         uint32_t mode = seg.mode;
@@ -308,7 +317,8 @@ sse_stream_kernel(const KParams P) {
                 }
                 // decode: one lane per line
                 uint32_t term_line = 0xFFFFu;
-                #pragma unroll 1
+                constexpr int UNROLL_DEC = SPLIT ? 2 : 1;   // the produce stage only writes a stub and a work item here
+                #pragma unroll UNROLL_DEC
                 for (int h = 0; h < 2; h++) {
                     int i = (int)lane + 32 * h;
                     if (i < n_lines && my_parse[h]) {

@@ -87,7 +87,6 @@ struct Lane {
     bool busy;
 };
 
-__device__ __forceinline__ void prefetch_l2(const uint8_t *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ uint4 ldcg16(const uint8_t *base, uint32_t off) {
     return __ldcg(reinterpret_cast<const uint4 *>(base + (off & ~15u)));
 }
