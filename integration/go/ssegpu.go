@@ -111,13 +111,14 @@ func (r *Result) Frames(i uint32, fn func(line []byte)) (terminated bool) {
 	segs := unsafe.Slice(r.r.segs, int(r.r.n_segs))
 	frames := unsafe.Slice(r.r.frames, int(r.r.n_frames))
 	runs := unsafe.Slice(r.r.runs, int(r.r.n_runs))
-	out := unsafe.Slice((*byte)(unsafe.Pointer(r.r.out)), int(r.r.out_bytes))
 	run := segs[i].run
 	for {
 		for k := run.frame_first; k < run.frame_first+run.frame_count; k++ {
 			f := frames[k]
+			// arena offset: >= in_base is a span of the batch's own input arena (zero-copy frame), else the out arena
+			src := unsafe.Slice((*byte)(unsafe.Pointer(C.sse_at(&r.r, f.off))), int(f.len))
 			line := make([]byte, int(f.len))
-			copy(line, out[f.off:f.off+f.len])
+			copy(line, src)
 			fn(line)
 		}
 		if run.next == C.SSE_NONE {
