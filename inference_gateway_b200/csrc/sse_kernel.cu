@@ -299,8 +299,9 @@ sse_stream_kernel(const KParams P) {
                         P.frames[fb + pre_f[h]] = f;
                     }
                 __syncwarp();
-                // emit: warp-cooperative serializer, frames back to back in line order
-                {
+                // emit: warp-cooperative serializer, frames back to back in line order (nothing to do when every frame of the
+                // round is a span of the input)
+                if (tot_b) {
                     uint32_t o = ob;
                     for (int i = 0; i < n_lines; i++) {
                         const LineEnt e = W.lt[i];

@@ -330,3 +330,27 @@ def test_zero_copy_frames_are_spans_of_the_input_arena():
                 assert all(o >= in_base for o in offs[0][1:]) and all(o >= in_base for o in offs[1][1:])
         finally:
             eng.close()
+
+
+def test_provider_hint_only_schedules(engine):
+    """sse_seg.provider feeds the decode kernel's work-item sort (lanes of a batch walk alike lines); results never depend on it."""
+    streams, _ = synth.make_config("C4", n_streams=96)
+    bodies = [b for b, _, _ in streams]
+    got = []
+    for hint in (0, 1, 2):
+        engine.reset_all()
+        slot, arena, segs = engine.acquire()
+        n, nb = engine.fill(arena, segs, [(c, R, b) for c, b in enumerate(bodies)])
+        segs["provider"][:n] = {0: 0, 1: np.arange(n) % 4, 2: np.random.default_rng(5).integers(0, 256, n)}[hint]
+        engine.submit(slot, n, nb)
+        res = engine.collect(slot)
+        try:
+            from tests.util import rec_to_dict
+            got.append([(res.seg_frames(i), [{k: v for k, v in rec_to_dict(res, r).items() if k != "frame"} for r in res.seg_recs(i)],
+                         int(res.segs[i]["flags"])) for i in range(n)])   # frame indices are bump-allocated: not comparable across runs
+        finally:
+            engine.release(slot)
+    assert got[0] == got[1] == got[2]
+    for i, b in enumerate(bodies):
+        v = orc.reframe(b)
+        assert got[0][i][0] == [l.out for l in v.lines if l.kind == orc.L_EMITTED]

@@ -43,7 +43,7 @@ def main():
                 if t < len(ev):
                     d = ev[t]
                     arena[off:off + len(d)] = np.frombuffer(d, dtype=np.uint8)
-                    segs[n] = (c, off, len(d), mode, 0, 0)
+                    segs[n] = (c, off, len(d), mode, c % 4, 0)   # provider hint: flavours cycle as in bench.py
                     off = (off + len(d) + 15) & ~15
                     n += 1
             t0 = time.perf_counter()

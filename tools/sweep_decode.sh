@@ -1,4 +1,3 @@
-for m in 3 0; do
-  timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-e2e --mode $m 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('mode $m', d['ms_per_step'])"
-done
 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+python bench.py --steps 50 --warmup 3 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; tail -c 600 gpurun_out/bench_1gpu.json
+python tools/latency_bench.py > gpurun_out/latency.json 2> gpurun_out/latency.err; tail -c 800 gpurun_out/latency.json
