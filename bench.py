@@ -27,6 +27,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly one JSON line: NCCL's version banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import numpy as np  # noqa: E402
 
 N_SLOTS = 3      # batches in flight on the end-to-end path: H2D, kernel and D2H of consecutive batches overlap
