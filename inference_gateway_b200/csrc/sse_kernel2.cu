@@ -32,6 +32,10 @@ constexpr int SEGSLOTS = 8;        // segments in flight per warp
 #define SSE_KSTEPS 2
 #endif
 constexpr int ROUNDS = SSE_ROUNDS;   // rounds between refills / busy checks
+#ifndef SSE_SKIPW
+#define SSE_SKIPW 2
+#endif
+constexpr int SKIPW = SSE_SKIPW;     // 16-byte windows a lane may cross per step while inside a long string value
 constexpr int KSTEPS = SSE_KSTEPS;   // plain automaton steps per round before the pending actions run
 
 struct SegSlot {
@@ -389,18 +393,22 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
     for (int k = 0; k < KSTEPS; k++) {
         if (L.p < L.pe && pend == 0) {
             if (L.st == S_VSTR && L.km == TRIE_DEAD) {
-                // inside a long string value: jump to the next '"', '\\', control or non-ASCII byte of the window
-                const uint32_t i = L.p & 15u;
-                unsigned long long lo = ((unsigned long long)special_mask4(L.win.y) << 32) | special_mask4(L.win.x);
-                unsigned long long hi = ((unsigned long long)special_mask4(L.win.w) << 32) | special_mask4(L.win.z);
-                if (i < 8) lo &= ~0ull << (i * 8); else { lo = 0; hi &= ~0ull << ((i - 8) * 8); }
-                uint32_t j = lo ? (uint32_t)(__ffsll((long long)lo) - 1) >> 3 : (hi ? 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3) : 16u);
-                uint32_t n = min(j - i, L.pe - L.p);
-                if (n) {
-                    L.p += n; L.slen += n;
-                    if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
-                    continue;
+                // inside a long string value: jump to the next '"', '\\', control or non-ASCII byte, up to SKIPW windows per step
+                bool adv = false;
+                #pragma unroll 1
+                for (int w = 0; w < SKIPW; w++) {
+                    const uint32_t i = L.p & 15u;
+                    unsigned long long lo = ((unsigned long long)special_mask4(L.win.y) << 32) | special_mask4(L.win.x);
+                    unsigned long long hi = ((unsigned long long)special_mask4(L.win.w) << 32) | special_mask4(L.win.z);
+                    if (i < 8) lo &= ~0ull << (i * 8); else { lo = 0; hi &= ~0ull << ((i - 8) * 8); }
+                    const uint32_t j = lo ? (uint32_t)(__ffsll((long long)lo) - 1) >> 3 : (hi ? 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3) : 16u);
+                    const uint32_t n = min(j - i, L.pe - L.p);
+                    if (n == 0) break;
+                    L.p += n; L.slen += n; adv = true;
+                    if ((L.p & 15u) != 0 || L.p >= L.pe) break;     // stopped at a special byte or at the end of the payload
+                    L.win = ldcg16(P.out, L.p);
                 }
+                if (adv) continue;
             }
             const uint32_t wsel = (L.p >> 2) & 3u;
             const uint32_t w01 = (wsel & 1u) ? L.win.y : L.win.x, w23 = (wsel & 1u) ? L.win.w : L.win.z;
