@@ -91,8 +91,15 @@ struct Lane {
     bool busy;
 };
 
-__device__ __forceinline__ uint4 ldcg16(const uint8_t *base, uint32_t off) {
-    return __ldcg(reinterpret_cast<const uint4 *>(base + (off & ~15u)));
+// RO = false: the bytes were written by another warp of the SAME kernel (fused v2): L2 only. RO = true: the payload arenas are
+// read-only for the whole decode kernel, so the window may be cached in L1 (SSE_LDWIN 1).
+#ifndef SSE_LDWIN
+#define SSE_LDWIN 1
+#endif
+template <bool RO>
+__device__ __forceinline__ uint4 ldwin16(const uint8_t *base, uint32_t off) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(base + (off & ~15u));
+    return (RO && SSE_LDWIN) ? __ldg(p) : __ldcg(p);
 }
 __device__ __forceinline__ bool lane_live(const Lane &L) {
     return L.sd >= 3 && ((L.sstk >> 10) & 31ull) == N_CHOICE && L.choices_count == 1;
@@ -387,6 +394,7 @@ __device__ void v2_finalize_segment(const KParams &P, SegSlot &sl) {
 }
 
 // One round of the per-lane automaton: KSTEPS plain steps, then the pending action (if any) of every lane.
+template <bool RO>
 __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J) {
     uint32_t pend = 0;                       // action | cls << 8 | in_str << 16 | in_tok << 17
     #pragma unroll
@@ -406,7 +414,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
                     if (n == 0) break;
                     L.p += n; L.slen += n; adv = true;
                     if ((L.p & 15u) != 0 || L.p >= L.pe) break;     // stopped at a special byte or at the end of the payload
-                    L.win = ldcg16(P.out, L.p);
+                    L.win = ldwin16<RO>(P.out, L.p);
                 }
                 if (adv) continue;
             }
@@ -424,7 +432,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
                 L.slen = in_tok ? L.slen + 1 : 0;
                 L.st = t;
                 L.p++;
-                if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
+                if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldwin16<RO>(P.out, L.p);
             } else pend = t | (cls << 8) | (in_str ? 0x10000u : 0u) | (in_tok ? 0x20000u : 0u);
         }
     }
@@ -442,7 +450,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
         L.sf = in_str ? (L.sf | nf) : (L.sf & ~SF_STRMASK);
         L.slen = (pend & 0x20000u) ? L.slen + 1 : 0;
         L.p++;
-        if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldcg16(P.out, L.p);
+        if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldwin16<RO>(P.out, L.p);
     }
 }
 
@@ -798,7 +806,7 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
                 L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
                 S.u_prompt = S.u_completion = S.u_total = 0;
                 L.busy = true;
-                if (L.p < L.pe) L.win = ldcg16(P.out, L.p);
+                if (L.p < L.pe) L.win = ldwin16<false>(P.out, L.p);
             }
         }
         if (all_idle) head += min(avail, 32u);
@@ -806,7 +814,7 @@ sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
         // every lane that stopped at an action runs it (all lanes dispatch together: the divergent part is shared)
         #pragma unroll 1
         for (int round = 0; round < ROUNDS; round++) {
-            v2_round(P, T, L, S, nullptr);
+            v2_round<false>(P, T, L, S, nullptr);
             if (L.busy && L.p >= L.pe) {
                 SegSlot &sl = W.slots[L.slot];
                 if (v2_finish_line(P, L, S, nullptr)) atomicMin(&sl.term, ((unsigned long long)L.rec << 32) | L.frame);
@@ -832,9 +840,10 @@ struct CtaSmem3 {
     DfaTables T;
     LaneScratch ls[V3_WARPS * 32];
     LaneJobs jobs[V3_WARPS * 32];
-    LaneTpl tpl[V3_WARPS * 32];
+    LaneTpl tpl[1];                 // V3_WARPS * 32 entries with SSE_FLAG_CHAINS (the launch sizes the dynamic part), else unused
 };
-static_assert(sizeof(CtaSmem3) <= 227 * 1024, "shared memory budget");
+constexpr size_t decode_smem_bytes(bool chains) { return sizeof(CtaSmem3) + (chains ? sizeof(LaneTpl) * (V3_WARPS * 32 - 1) : 0); }
+static_assert(decode_smem_bytes(true) <= 227 * 1024, "shared memory budget");
 
 __global__ void __launch_bounds__(V3_WARPS * 32, 1)
 sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
@@ -849,7 +858,7 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
     const DfaTables &T = cs.T;
     LaneScratch &S = cs.ls[threadIdx.x];
     LaneJobs *J = &cs.jobs[threadIdx.x];
-    LaneTpl &Tp = cs.tpl[threadIdx.x];
+    LaneTpl &Tp = cs.tpl[(P.flags & SSE_FLAG_CHAINS) ? threadIdx.x : 0];   // only touched with CHAINS
     LaneJobs *Jw = &cs.jobs[threadIdx.x & ~31u];   // this warp's 32 queues
     J->n = 0;
     const uint32_t lane = lane_id();
@@ -881,7 +890,7 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
             S.u_prompt = S.u_completion = S.u_total = 0;
             L.busy = true;
             if (L.p < L.pe) {
-                L.win = ldcg16(P.out, L.p);
+                L.win = ldwin16<true>(P.out, L.p);
                 // items are grouped by shape, not by address: pull the rest of the payload towards L2 ahead of the automaton
                 if (sorted) for (uint32_t q = (L.p & ~127u) + 128u; q < L.pe && q < L.p + 1024u; q += 128u) prefetch_l2(P.out + q);
             }
@@ -889,7 +898,7 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
         while (__any_sync(FULL, L.busy)) {
             #pragma unroll 1
             for (int round = 0; round < ROUNDS; round++) {
-                v2_round(P, T, L, S, J);
+                v2_round<true>(P, T, L, S, J);
                 if (L.busy && L.p >= L.pe) {
                     if (v2_finish_line(P, L, S, J, chains ? &Tp : nullptr)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
                     L.p = L.pe = 0;
@@ -918,7 +927,7 @@ sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
                             L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
                             S.u_prompt = S.u_completion = S.u_total = 0;
                             L.busy = true;
-                            if (L.p < L.pe) L.win = ldcg16(P.out, L.p);
+                            if (L.p < L.pe) L.win = ldwin16<true>(P.out, L.p);
                             break;
                         }
                     }
@@ -1076,7 +1085,7 @@ int sse_v2_prepare(int device) {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(sse_stream_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem2));
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(sse_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
+    e = cudaFuncSetAttribute(sse_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem_bytes(true));
     if (e != cudaSuccess) return (int)e;
     g_tables_dev[device] = d;
     return 0;
@@ -1094,7 +1103,7 @@ int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int
     sse_bucket_hist_kernel<<<sm_count * 2, 512, 0, (cudaStream_t)stream>>>(p);
     sse_bucket_scan_kernel<<<1, SCAN_TPB, 0, (cudaStream_t)stream>>>(p);
     sse_bucket_scatter_kernel<<<sm_count * 2, SCATTER_TPB, 0, (cudaStream_t)stream>>>(p);
-    sse_decode_kernel<<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
+    sse_decode_kernel<<<sm_count, V3_WARPS * 32, decode_smem_bytes((p.flags & SSE_FLAG_CHAINS) != 0), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const int tpb = 256;

@@ -1,7 +1,3 @@
-for cfg in "-DSSE_SKIPW=1" "-DSSE_SKIPW=2" "-DSSE_SKIPW=4" "-DSSE_SKIPW=8"; do
-  SSE_NVCC_DEFS="$cfg" python inference_gateway_b200/build.py --force > /dev/null 2>&1 || echo "build failed $cfg"
-  timeout 200 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$cfg bench', d['ms_per_step'])"
-  python tools/tick_bench.py 2>/dev/null | tail -1
-done
-python inference_gateway_b200/build.py --force > /dev/null 2>&1
 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+timeout 200 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['ms_per_step'])"
+python tools/tick_bench.py 2>/dev/null | tail -1
