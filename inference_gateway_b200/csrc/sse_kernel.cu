@@ -24,7 +24,7 @@ namespace {
 #endif
 template <bool SPLIT>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, SSE_V1_MINB)
-sse_stream_kernel(const KParams P) {
+sse_stream_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaSmem &cs = *reinterpret_cast<CtaSmem *>(smem_raw);
     {   // schema table: constant -> shared (lanes index it divergently)

@@ -112,17 +112,24 @@ __device__ __forceinline__ void value_done(Lane &L) {
     L.st = ((bits >> (d & 63u)) & 1ull) ? (uint32_t)S_AFTA : (uint32_t)S_AFTO;
 }
 
+// Span of a captured string: without escapes it is the payload's own bytes (no call, nothing through local memory); the
+// rare decoded case goes through capture() (text-arena allocation + queued warp-cooperative unquote).
+__device__ __forceinline__ Span capture_v2(const KParams &P, LaneJobs *J, uint32_t s, uint32_t e, int dec, uint32_t *patch) {
+    if (!dec) { Span r; r.off = s; r.len = e - s; r.text = false; return r; }
+    ParseCtx cx; cx.jobs = J; cx.sm = P.out; cx.P = &P; cx.S = nullptr; cx.emitted = true; cx.out_delta = 0;
+    return capture(cx, (int)s, (int)e, dec, patch);
+}
+
 __device__ void v2_flush_tc(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
     if ((S.tc_flags & SSE_TC_HAS_ID) || ((S.tc_flags & SSE_TC_HAS_FUNC) && (S.name_len || S.args_len))) L.sf |= SF_TCVALID;
     L.sf &= ~SF_TCOPEN;
     uint32_t idx = atomicAdd(&P.ctr->n_tcs, 1u);
     if (idx >= P.cap_tcs) { sse_overflow(P.ctr, SSE_OVF_TCS); return; }
     sse_tc *rec = &P.tcs[idx];
-    ParseCtx cx; cx.jobs = J; cx.sm = P.out; cx.P = &P; cx.S = nullptr; cx.emitted = true; cx.out_delta = 0;
-    Span id = capture(cx, (int)S.id_off, (int)(S.id_off + S.id_len), S.tc_dec & 3, &rec->id_len);
-    Span ty = capture(cx, (int)S.type_off, (int)(S.type_off + S.type_len), (S.tc_dec >> 2) & 3, &rec->type_len);
-    Span nm = capture(cx, (int)S.name_off, (int)(S.name_off + S.name_len), (S.tc_dec >> 4) & 3, &rec->name_len);
-    Span ar = capture(cx, (int)S.args_off, (int)(S.args_off + S.args_len), (S.tc_dec >> 6) & 3, &rec->args_len);
+    Span id = capture_v2(P, J, S.id_off, S.id_off + S.id_len, S.tc_dec & 3, &rec->id_len);
+    Span ty = capture_v2(P, J, S.type_off, S.type_off + S.type_len, (S.tc_dec >> 2) & 3, &rec->type_len);
+    Span nm = capture_v2(P, J, S.name_off, S.name_off + S.name_len, (S.tc_dec >> 4) & 3, &rec->name_len);
+    Span ar = capture_v2(P, J, S.args_off, S.args_off + S.args_len, (S.tc_dec >> 6) & 3, &rec->args_len);
     sse_tc o;
     o.index = S.tc_index;
     o.flags = S.tc_flags | (id.text ? SSE_TC_ID_TEXT : 0) | (ty.text ? SSE_TC_TYPE_TEXT : 0) |
@@ -337,9 +344,8 @@ __device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJo
             } else sse_overflow(P.ctr, SSE_OVF_USAGES);
         }
         if (L.n_choices > 0) {
-            ParseCtx cx; cx.jobs = J; cx.sm = P.out; cx.P = &P; cx.S = nullptr; cx.emitted = true; cx.out_delta = 0;
-            Span ct = capture(cx, (int)L.content_off, (int)(L.content_off + L.content_len), ((L.sf & SF_CDEC) ? 1 : 0) | ((L.sf & SF_CBAD) ? 2 : 0),
-                              &P.recs[L.rec].content_len);
+            Span ct = capture_v2(P, J, L.content_off, L.content_off + L.content_len, ((L.sf & SF_CDEC) ? 1 : 0) | ((L.sf & SF_CBAD) ? 2 : 0),
+                                 &P.recs[L.rec].content_len);
             r.content_off = ct.len ? ct.off : 0; r.content_len = ct.len;
             if (ct.text && ct.len) r.flags |= SSE_F_CONTENT_TEXT;
             r.flags |= L.finish << SSE_F_FINISH_SHIFT;
@@ -464,7 +470,7 @@ struct Producer {                  // warp-uniform coroutine state of the segmen
 };
 
 __global__ void __launch_bounds__(V2_WARPS * 32, 1)
-sse_stream_kernel_v2(const KParams P, const DfaTables *__restrict__ gT) {
+sse_stream_kernel_v2(const __grid_constant__ KParams P, const DfaTables *__restrict__ gT) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaSmem2 &cs = *reinterpret_cast<CtaSmem2 *>(smem_raw);
     {
@@ -846,7 +852,7 @@ constexpr size_t decode_smem_bytes(bool chains) { return sizeof(CtaSmem3) + (cha
 static_assert(decode_smem_bytes(true) <= 227 * 1024, "shared memory budget");
 
 __global__ void __launch_bounds__(V3_WARPS * 32, 1)
-sse_decode_kernel(const KParams P, const DfaTables *__restrict__ gT) {
+sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict__ gT) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaSmem3 &cs = *reinterpret_cast<CtaSmem3 *>(smem_raw);
     {
