@@ -8,7 +8,10 @@
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 8;
+#ifndef SSE_V1_WARPS
+#define SSE_V1_WARPS 10
+#endif
+constexpr int WARPS_PER_CTA = SSE_V1_WARPS;
 constexpr int BUF = 8192;          // line window per warp (bytes, multiple of 16)
 constexpr int LT_MAX = 64;         // lines per round
 constexpr int DONE_MAX = 16;
@@ -82,6 +85,7 @@ struct LineEnt {
     uint16_t ndeps;     // head: number of dependents that follow it
     uint16_t chain;     // 0 head, 1 dependent
     uint16_t zc;        // 1: the frame's bytes stand in the input arena as they are (no copy; offsets are input offsets)
+    uint16_t clen;      // bytes this line occupies in the out arena (frame, or the payload of a swallowed line that is decoded)
 };
 enum : uint8_t { K_DROP = 0, K_EMIT = 1, K_DONE = 2, K_DONE_EXACT = 3 };
 

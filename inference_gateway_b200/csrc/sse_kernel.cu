@@ -178,7 +178,7 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                 const int n_done = min((int)W.done_cnt, DONE_MAX);
 
                 // classify: one lane per line (2 passes for 64 lines)
-                uint32_t my_flen[2] = { 0, 0 }, my_kind[2] = { 0, 0 }, my_parse[2] = { 0, 0 }, my_zc[2] = { 0, 0 };
+                uint32_t my_flen[2] = { 0, 0 }, my_kind[2] = { 0, 0 }, my_parse[2] = { 0, 0 }, my_zc[2] = { 0, 0 }, my_clen[2] = { 0, 0 };
                 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     int i = (int)lane + 32 * h;
@@ -198,6 +198,7 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                                 pay_s = pref ? a + 6 : a; pay_e = b;
                                 bool exact = (pay_e - pay_s) == 6 && is_done_at(buf + pay_s);
                                 kind = exact ? K_DONE_EXACT : K_DONE; parse = 1;
+                                zc = (zero_copy && pay_s >= zc_lo) ? 1u : 0u;   // split: decoded in place by the decode kernel
                             } else if (pref && b - a > 6) {                  // agent.go:190-197
                                 kind = K_EMIT; src_s = a; pay_s = a + 6; pay_e = b; flen = (b - a) + 2; parse = 1;
                                 // "data: " + payload + "\n\n" is already what the input holds when nothing was trimmed
@@ -211,15 +212,18 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                         }
                         LineEnt &e = W.lt[i];
                         e.src_s = (uint16_t)src_s; e.pay_s = (uint16_t)pay_s; e.pay_e = (uint16_t)pay_e;
-                        e.flen = (uint16_t)flen; e.kind = (uint8_t)kind; e.parse = (uint8_t)parse; e.zc = (uint16_t)zc;
-                        my_flen[h] = (uint32_t)flen; my_kind[h] = kind; my_parse[h] = parse; my_zc[h] = zc;
+                        // bytes to materialise: a frame that is not a span of the input; in the split pipeline also the payload of a
+                        // swallowed "[DONE]"-containing line (agent.go:182: still parsed), which the decode kernel reads from an arena
+                        const int clen = zc ? 0 : (flen ? flen : ((SPLIT && kind == K_DONE) ? pay_e - pay_s : 0));
+                        e.flen = (uint16_t)flen; e.kind = (uint8_t)kind; e.parse = (uint8_t)parse; e.zc = (uint16_t)zc; e.clen = (uint16_t)clen;
+                        my_flen[h] = (uint32_t)flen; my_kind[h] = kind; my_parse[h] = parse; my_zc[h] = zc; my_clen[h] = (uint32_t)clen;
                     }
                 }
                 // allocate: exclusive prefix (line order) of frame bytes / frame count / rec count
                 uint32_t pre_b[2], pre_f[2], pre_r[2], tot_b = 0, tot_f = 0, tot_r = 0;
                 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    uint32_t vb = my_zc[h] ? 0u : my_flen[h], vf = my_flen[h] ? 1u : 0u, vr = my_parse[h];
+                    uint32_t vb = my_clen[h], vf = my_flen[h] ? 1u : 0u, vr = my_parse[h];
                     uint32_t sb = vb, sf = vf, sr = vr;
                     #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
@@ -236,7 +240,7 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                     // every decoded line is its own work item: index = rank among this round's emitted data lines
                     uint32_t my_q = 0;
                     #pragma unroll
-                    for (int h = 0; h < 2; h++) my_q += (my_parse[h] && my_kind[h] == K_EMIT) ? 1u : 0u;
+                    for (int h = 0; h < 2; h++) my_q += (my_parse[h] && (my_kind[h] == K_EMIT || my_kind[h] == K_DONE)) ? 1u : 0u;
                     uint32_t pre_q = my_q;
                     #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, pre_q, d); if ((int)lane >= d) pre_q += t; }
@@ -245,9 +249,9 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                     #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         int i = (int)lane + 32 * h;
-                        if (i < n_lines && my_parse[h] && my_kind[h] == K_EMIT) {
+                        if (i < n_lines && my_parse[h] && (my_kind[h] == K_EMIT || my_kind[h] == K_DONE)) {
                             LineEnt &w = W.lt[i];
-                            w.chain = 0; w.rel = (uint16_t)(pre_q + ((h == 1 && my_parse[0] && my_kind[0] == K_EMIT) ? 1u : 0u)); w.dfirst = 0; w.ndeps = 0;
+                            w.chain = 0; w.rel = (uint16_t)(pre_q + ((h == 1 && my_parse[0] && (my_kind[0] == K_EMIT || my_kind[0] == K_DONE)) ? 1u : 0u)); w.dfirst = 0; w.ndeps = 0;
                         }
                     }
                     __syncwarp();
@@ -256,9 +260,9 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                     uint32_t cur_deps = 0;
                     for (int i = 0; i < n_lines; i++) {
                         const LineEnt e = W.lt[i];
-                        if (!(e.parse && e.kind == K_EMIT)) continue;
+                        if (!(e.parse && (e.kind == K_EMIT || e.kind == K_DONE))) continue;
                         bool dep = false; int cp = 0, cs = 0;
-                        if (prev >= 0) {
+                        if (prev >= 0 && e.kind == K_EMIT) {   // a swallowed line is always a head and never a template
                             const LineEnt pe = W.lt[prev];
                             dep = chain_compare(buf, W.spec, e.pay_s, e.pay_e - e.pay_s, pe.pay_s, pe.pay_e - pe.pay_s, cp, cs);
                         }
@@ -271,7 +275,7 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                             }
                         }
                         if (dep) { tot_d++; cur_deps++; } else { tot_q++; cur_head = i; cur_deps = 0; }
-                        prev = i;
+                        prev = (e.kind == K_EMIT) ? i : -1;
                     }
                     if (lane == 0 && cur_head >= 0) W.lt[cur_head].ndeps = (uint16_t)cur_deps;
                     __syncwarp();
@@ -305,15 +309,15 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                     uint32_t o = ob;
                     for (int i = 0; i < n_lines; i++) {
                         const LineEnt e = W.lt[i];
-                        if (!e.flen || e.zc) continue;
+                        if (!e.clen) continue;
                         uint8_t *dst = P.out + o;
-                        const uint8_t *sp = buf + e.src_s;
-                        if (mode & SSE_MODE_R) {
+                        if (!e.flen) copy_s2g_vec(dst, buf + e.pay_s, (int)e.clen);   // payload of a swallowed line (no frame)
+                        else if (mode & SSE_MODE_R) {
                             const int body = (int)e.flen - 2;      // "data: " + payload is contiguous in the window
-                            copy_s2g_vec(dst, sp, body);
+                            copy_s2g_vec(dst, buf + e.src_s, body);
                             if (lane < 2) dst[body + lane] = (uint8_t)'\n';
-                        } else copy_s2g_vec(dst, sp, (int)e.flen);
-                        o += e.flen;
+                        } else copy_s2g_vec(dst, buf + e.src_s, (int)e.flen);
+                        o += e.clen;
                     }
                 }
                 // decode: one lane per line
@@ -326,10 +330,12 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                         const LineEnt e = W.lt[i];
                         ParseCtx cx; cx.sm = buf; cx.P = &P; cx.S = &cs.schema;
                         cx.emitted = my_kind[h] == K_EMIT;
-                        cx.out_delta = e.zc ? (int64_t)P.in_base + in_delta : (int64_t)(ob + pre_b[h]) - (int64_t)e.src_s;
-                        if (SPLIT && my_kind[h] == K_EMIT) {
+                        cx.out_delta = e.zc ? (int64_t)P.in_base + in_delta
+                                            : (int64_t)(ob + pre_b[h]) - (int64_t)(e.flen ? e.src_s : e.pay_s);
+                        if (SPLIT && (my_kind[h] == K_EMIT || my_kind[h] == K_DONE)) {
+                            const bool swallowed = my_kind[h] == K_DONE;
                             sse_rec stub;
-                            stub.frame = fb + pre_f[h]; stub.flags = 0; stub.content_off = stub.content_len = 0; stub.tc_first = SSE_NONE;
+                            stub.frame = swallowed ? SSE_NONE : fb + pre_f[h]; stub.flags = 0; stub.content_off = stub.content_len = 0; stub.tc_first = SSE_NONE;
                             stub.tc_count = 0; stub.n_choices = 0; stub.usage = SSE_NONE; stub.payload_len = (uint32_t)(e.pay_e - e.pay_s);
                             P.recs[rb + pre_r[h]] = stub;
                             uint4 it;
@@ -339,7 +345,8 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                                 // shape class; the second decoded line of a round (first content delta, the longest) sorts first: long work early
                                 const uint32_t ord = min((uint32_t)e.rel, 7u);
                                 const uint32_t cls = ((ord == 1u ? 0u : (ord == 0u ? 1u : ord)) << 2) | (seg.provider & 3u);
-                                it.y = (uint32_t)(e.pay_e - e.pay_s) | (cls << 24) | ((mode & SSE_MODE_R) ? 0x80000000u : 0u);
+                                // bit 31: the line can terminate the stream (emitted, mode R); bit 30: swallowed line (SSE_F_DONE_LINE)
+                                it.y = (uint32_t)(e.pay_e - e.pay_s) | (cls << 24) | (swallowed ? 0x40000000u : ((mode & SSE_MODE_R) ? 0x80000000u : 0u));
                                 it.w = s;
                                 P.items[qb + e.rel] = it;
                                 if (P.flags & SSE_FLAG_CHAINS) P.item_deps[qb + e.rel] = make_uint2(db + e.dfirst, e.ndeps);
@@ -351,7 +358,8 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                             continue;
                         }
                         ParseOut po;
-                        if (my_kind[h] == K_DONE_EXACT) { po.flags = 0; po.content_off = po.content_len = 0; po.tc_first = SSE_NONE; po.tc_count = po.n_choices = 0; po.usage = SSE_NONE; }
+                        // (split pipeline: only exact "[DONE]" payloads get here, the sequential decoder is not part of that kernel)
+                        if (SPLIT || my_kind[h] == K_DONE_EXACT) { po.flags = 0; po.content_off = po.content_len = 0; po.tc_first = SSE_NONE; po.tc_count = po.n_choices = 0; po.usage = SSE_NONE; }
                         else decode_chunk(cx, e.pay_s, e.pay_e, po);
                         sse_rec r;
                         r.frame = cx.emitted ? fb + pre_f[h] : SSE_NONE;

@@ -78,7 +78,7 @@ static_assert(sizeof(CtaSmem2) <= 227 * 1024, "shared memory budget");
 // per-string flags (cleared outside strings) and per-line flags
 constexpr uint32_t SF_ESC = 1, SF_HI = 2, SF_UPPER = 4, SF_BAD = 8, SF_STRMASK = 15;
 constexpr uint32_t SF_SYN = 0x100, SF_TYPE = 0x200, SF_DEPTH = 0x400, SF_GBAD = 0x800, SF_USAGE = 0x1000,
-                   SF_TCNONNIL = 0x2000, SF_TCOPEN = 0x4000, SF_TCVALID = 0x8000, SF_CDEC = 0x10000, SF_RMODE = 0x20000, SF_CBAD = 0x40000, SF_CSET = 0x80000;
+                   SF_TCNONNIL = 0x2000, SF_TCOPEN = 0x4000, SF_TCVALID = 0x8000, SF_CDEC = 0x10000, SF_RMODE = 0x20000, SF_CBAD = 0x40000, SF_CSET = 0x80000, SF_DONELINE = 0x100000;
 
 struct Lane {
     uint32_t p, pe;                // out-arena offsets of the payload being decoded
@@ -333,6 +333,7 @@ __device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJo
     r.frame = L.frame; r.flags = 0; r.content_off = r.content_len = 0; r.tc_first = SSE_NONE; r.tc_count = 0; r.n_choices = 0;
     r.usage = SSE_NONE;
     if (L.sf & SF_DEPTH) r.flags |= SSE_F_DEPTH_LIMIT;
+    if (L.sf & SF_DONELINE) r.flags |= SSE_F_DONE_LINE;      // swallowed by the reframe, parsed for agent.go:377-402
     if (!(L.sf & (SF_SYN | SF_TYPE))) {
         r.flags |= SSE_F_JSON_OK;
         r.n_choices = (uint16_t)min(L.n_choices, 0xFFFFu);
@@ -890,7 +891,7 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
             L.dep_first = L.dep_cnt = 0;
             if (sorted) { const uint2 dd = P.item_deps_sorted[idx]; L.dep_first = dd.x; L.dep_cnt = dd.y; if (dd.y) prefetch_l2(reinterpret_cast<const uint8_t *>(&P.deps[dd.x])); }
             L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.km = TRIE_ROOT; L.slen = 0;
-            L.sf = (it.y & 0x80000000u) ? SF_RMODE : 0u;
+            L.sf = ((it.y & 0x80000000u) ? SF_RMODE : 0u) | ((it.y & 0x40000000u) ? SF_DONELINE : 0u);
             L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
             L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
             S.u_prompt = S.u_completion = S.u_total = 0;
