@@ -331,7 +331,7 @@ def main():
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if tj.get("workload") == args.workload and tj.get("streams") == args.streams:
+        if tj.get("workload") == args.workload and tj.get("streams") == args.streams and args.mode == 3 and not args.flags:
             traffic = tj.get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
