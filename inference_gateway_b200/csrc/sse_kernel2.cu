@@ -33,7 +33,7 @@ constexpr int SEGSLOTS = 8;        // segments in flight per warp
 #endif
 constexpr int ROUNDS = SSE_ROUNDS;   // rounds between refills / busy checks
 #ifndef SSE_SKIPW
-#define SSE_SKIPW 2
+#define SSE_SKIPW 4
 #endif
 constexpr int SKIPW = SSE_SKIPW;     // 16-byte windows a lane may cross per step while inside a long string value
 constexpr int KSTEPS = SSE_KSTEPS;   // plain automaton steps per round before the pending actions run
@@ -404,27 +404,28 @@ __device__ void v2_finalize_segment(const KParams &P, SegSlot &sl) {
 template <bool RO>
 __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J) {
     uint32_t pend = 0;                       // action | cls << 8 | in_str << 16 | in_tok << 17
+    // phase A (once per round, only the lanes inside a long string value): jump to the next '"', '\\', control or non-ASCII
+    // byte, up to SKIPW windows. Keeping it out of the step loop means a warp whose lanes are not all in the same phase
+    // executes this path once per round, not once per step.
+    if (L.p < L.pe && L.st == S_VSTR && L.km == TRIE_DEAD) {
+        #pragma unroll 1
+        for (int w = 0; w < SKIPW; w++) {
+            const uint32_t i = L.p & 15u;
+            unsigned long long lo = ((unsigned long long)special_mask4(L.win.y) << 32) | special_mask4(L.win.x);
+            unsigned long long hi = ((unsigned long long)special_mask4(L.win.w) << 32) | special_mask4(L.win.z);
+            if (i < 8) lo &= ~0ull << (i * 8); else { lo = 0; hi &= ~0ull << ((i - 8) * 8); }
+            const uint32_t j = lo ? (uint32_t)(__ffsll((long long)lo) - 1) >> 3 : (hi ? 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3) : 16u);
+            const uint32_t n = min(j - i, L.pe - L.p);
+            if (n == 0) break;
+            L.p += n; L.slen += n;
+            if ((L.p & 15u) != 0 || L.p >= L.pe) break;     // stopped at a special byte or at the end of the payload
+            L.win = ldwin16<RO>(P.out, L.p);
+        }
+    }
+    // phase B: plain automaton steps
     #pragma unroll
     for (int k = 0; k < KSTEPS; k++) {
         if (L.p < L.pe && pend == 0) {
-            if (L.st == S_VSTR && L.km == TRIE_DEAD) {
-                // inside a long string value: jump to the next '"', '\\', control or non-ASCII byte, up to SKIPW windows per step
-                bool adv = false;
-                #pragma unroll 1
-                for (int w = 0; w < SKIPW; w++) {
-                    const uint32_t i = L.p & 15u;
-                    unsigned long long lo = ((unsigned long long)special_mask4(L.win.y) << 32) | special_mask4(L.win.x);
-                    unsigned long long hi = ((unsigned long long)special_mask4(L.win.w) << 32) | special_mask4(L.win.z);
-                    if (i < 8) lo &= ~0ull << (i * 8); else { lo = 0; hi &= ~0ull << ((i - 8) * 8); }
-                    const uint32_t j = lo ? (uint32_t)(__ffsll((long long)lo) - 1) >> 3 : (hi ? 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3) : 16u);
-                    const uint32_t n = min(j - i, L.pe - L.p);
-                    if (n == 0) break;
-                    L.p += n; L.slen += n; adv = true;
-                    if ((L.p & 15u) != 0 || L.p >= L.pe) break;     // stopped at a special byte or at the end of the payload
-                    L.win = ldwin16<RO>(P.out, L.p);
-                }
-                if (adv) continue;
-            }
             const uint32_t wsel = (L.p >> 2) & 3u;
             const uint32_t w01 = (wsel & 1u) ? L.win.y : L.win.x, w23 = (wsel & 1u) ? L.win.w : L.win.z;
             const uint32_t w = (wsel & 2u) ? w23 : w01;
