@@ -411,8 +411,15 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
         #pragma unroll 1
         for (int w = 0; w < SKIPW; w++) {
             const uint32_t i = L.p & 15u;
-            unsigned long long lo = ((unsigned long long)special_mask4(L.win.y) << 32) | special_mask4(L.win.x);
-            unsigned long long hi = ((unsigned long long)special_mask4(L.win.w) << 32) | special_mask4(L.win.z);
+            const uint32_t s0 = special_mask4(L.win.x), s1 = special_mask4(L.win.y), s2 = special_mask4(L.win.z), s3 = special_mask4(L.win.w);
+            if (i == 0 && (s0 | s1 | s2 | s3) == 0 && L.p + 16u <= L.pe) {      // a whole window of plain string bytes
+                L.p += 16u; L.slen += 16u;
+                if (L.p >= L.pe) break;
+                L.win = ldwin16<RO>(P.out, L.p);
+                continue;
+            }
+            unsigned long long lo = ((unsigned long long)s1 << 32) | s0;
+            unsigned long long hi = ((unsigned long long)s3 << 32) | s2;
             if (i < 8) lo &= ~0ull << (i * 8); else { lo = 0; hi &= ~0ull << ((i - 8) * 8); }
             const uint32_t j = lo ? (uint32_t)(__ffsll((long long)lo) - 1) >> 3 : (hi ? 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3) : 16u);
             const uint32_t n = min(j - i, L.pe - L.p);
