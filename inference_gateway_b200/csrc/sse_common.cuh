@@ -106,11 +106,22 @@ struct CtaSmem {
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ void prefetch_l2(const uint8_t *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
+// 0x80 in every byte of x that is zero (exact)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) { return ~((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x)) & 0x80808080u; }
+// bits 7, 15, 23, 31 -> bits 0..3
+__device__ __forceinline__ uint32_t gather4(uint32_t z) { return (((z >> 7) * 0x00204081u) >> 21) & 0xFu; }
 // 4-bit mask of the bytes of w equal to the byte replicated in pat
-__device__ __forceinline__ uint32_t eqmask4(uint32_t w, uint32_t pat) {
-    const uint32_t x = w ^ pat;                                             // zero byte <=> equal
-    const uint32_t z = ~((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x)) & 0x80808080u;   // exact: 0x80 where the byte of x is zero
-    return (((z >> 7) * 0x00204081u) >> 21) & 0xFu;
+__device__ __forceinline__ uint32_t eqmask4(uint32_t w, uint32_t pat) { return gather4(zero_bytes(w ^ pat)); }
+// 16-bit mask of the positions in v where '[' is followed by 'D' (position 15 cannot see its successor: any '[' there counts).
+// A cheap superset of the places where "[DONE]" can start; 0 for almost every chunk of a JSON stream.
+__device__ __forceinline__ uint32_t done_candidates16(const uint4 &v) {
+    const uint32_t b0 = zero_bytes(v.x ^ 0x5B5B5B5Bu), b1 = zero_bytes(v.y ^ 0x5B5B5B5Bu), b2 = zero_bytes(v.z ^ 0x5B5B5B5Bu), b3 = zero_bytes(v.w ^ 0x5B5B5B5Bu);
+    if ((b0 | b1 | b2 | b3) == 0) return 0;
+    const uint32_t d0 = zero_bytes(v.x ^ 0x44444444u), d1 = zero_bytes(v.y ^ 0x44444444u), d2 = zero_bytes(v.z ^ 0x44444444u), d3 = zero_bytes(v.w ^ 0x44444444u);
+    const uint32_t c0 = b0 & ((d0 >> 8) | (d1 << 24)), c1 = b1 & ((d1 >> 8) | (d2 << 24)), c2 = b2 & ((d2 >> 8) | (d3 << 24));
+    const uint32_t c3 = b3 & ((d3 >> 8) | 0x80000000u);
+    if ((c0 | c1 | c2 | c3) == 0) return 0;
+    return gather4(c0) | (gather4(c1) << 4) | (gather4(c2) << 8) | (gather4(c3) << 12);
 }
 __device__ __forceinline__ uint32_t eqmask16(const uint4 &v, uint32_t pat) {
     return eqmask4(v.x, pat) | (eqmask4(v.y, pat) << 4) | (eqmask4(v.z, pat) << 8) | (eqmask4(v.w, pat) << 12);

@@ -142,7 +142,7 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                     if (off < fill) {
                         uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
                         nlm = eqmask16(v, 0x0A0A0A0Au);
-                        if (mode & SSE_MODE_R) brm = eqmask16(v, 0x5B5B5B5Bu);
+                        if (mode & SSE_MODE_R) brm = done_candidates16(v);
                         if (SPLIT && (mode & SSE_MODE_PARSE) && (P.flags & SSE_FLAG_CHAINS)) W.spec[off >> 4] = (uint16_t)special_bits16(v);
                         // mask bytes outside [pos, fill)
                         uint32_t valid = 0xFFFFu;

@@ -354,3 +354,19 @@ def test_provider_hint_only_schedules(engine):
     for i, b in enumerate(bodies):
         v = orc.reframe(b)
         assert got[0][i][0] == [l.out for l in v.lines if l.kind == orc.L_EMITTED]
+
+
+def test_done_marker_at_every_alignment(engine):
+    """agent.go:181 is a substring test: "[DONE]" anywhere in the trimmed line swallows it. The produce scan finds candidates
+    16 bytes per lane ('[' followed by 'D', with the chunk's last byte handled conservatively): every alignment of the
+    marker relative to the 16-byte chunks, near misses, and markers split by a batch boundary must agree with the oracle."""
+    bodies = []
+    for pad in range(0, 40):
+        fill = "x" * pad
+        for marker in ("[DONE]", "[DONE", "[D", "[", "[DONEE]", "[done]", "[[DONE]]", "[D[DONE]"):
+            bodies.append(('data: {"choices":[{"delta":{"content":"%s%s tail"}}]}\n\n' % (fill, marker)).encode() +
+                          b'data: {"choices":[{"delta":{"content":"next"}}]}\n\n')
+    bodies.append(b"data: " + b"[" * 70 + b"DONE]\n\n" + b"data: {}\n\n")
+    bodies.append(b"[DONE]\n[DONE]\n\ndata: x[DONE]\n\n   data: [DONE]   \n\ndata: {\"a\":1}\n\n")
+    for nb in (1, 2, 3):
+        _run_and_check(engine, bodies, [R] * len(bodies), n_batches=nb, seed=60 + nb)
