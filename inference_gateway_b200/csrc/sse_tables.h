@@ -98,10 +98,11 @@ inline int build_tables(DfaTables &T, const FieldSrc *fields, int n_fields, cons
     for (int s : { (int)S_VAL, (int)S_ARR0, (int)S_OBJ0, (int)S_KEY, (int)S_COLON, (int)S_AFTO, (int)S_AFTA, (int)S_END })
         for (int c : ws) set(s, c, (uint8_t)s);
     auto value_start = [&](int s, bool redo) {
-        set(s, C_LBRACE, redo ? A_ELEM_REDO : A_OPEN_OBJ); set(s, C_LBRACK, redo ? A_ELEM_REDO : A_OPEN_ARR);
-        set(s, C_QUOTE, redo ? A_ELEM_REDO : S_VSTR); set(s, C_MINUS, redo ? A_ELEM_REDO : S_NMINUS);
-        set(s, C_ZERO, redo ? A_ELEM_REDO : S_NZERO); set(s, C_DIGIT, redo ? A_ELEM_REDO : S_NINT);
-        set(s, C_t, redo ? A_ELEM_REDO : S_T1); set(s, C_f, redo ? A_ELEM_REDO : S_F1); set(s, C_n, redo ? A_ELEM_REDO : S_N1);
+        auto tgt = [&](int t) { return redo ? (int)A_ELEM_REDO : t; };   // states and actions share one byte of the table
+        set(s, C_LBRACE, tgt(A_OPEN_OBJ)); set(s, C_LBRACK, tgt(A_OPEN_ARR));
+        set(s, C_QUOTE, tgt(S_VSTR)); set(s, C_MINUS, tgt(S_NMINUS));
+        set(s, C_ZERO, tgt(S_NZERO)); set(s, C_DIGIT, tgt(S_NINT));
+        set(s, C_t, tgt(S_T1)); set(s, C_f, tgt(S_F1)); set(s, C_n, tgt(S_N1));
     };
     value_start(S_VAL, false);
     value_start(S_ARR0, true);
