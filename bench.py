@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--streams", type=int, default=65536, help="concurrent streams per GPU")
     ap.add_argument("--workload", default="C4")
     ap.add_argument("--mode", type=int, default=None, help="override the workload's mode bits (0 P, 2 P+parse, 3 R+parse)")
-    ap.add_argument("--flags", type=int, default=0, help="sse_config.flags (1 v1 kernel, 2 fused v2 kernel, 4 chains experiment)")
+    ap.add_argument("--flags", type=int, default=0, help="sse_config.flags (1 v1 kernel, 2 fused v2 kernel, 8 copy-out)")
     ap.add_argument("--n-content", type=int, default=None, help="content deltas per stream (default: the config's 7)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

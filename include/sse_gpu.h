@@ -68,8 +68,6 @@ typedef struct {
 } sse_config;
 
 #define SSE_FLAG_KERNEL_V1 1u  /* fused first-generation kernel (sequential per-lane decoder) */
-#define SSE_FLAG_CHAINS 4u     /* split pipeline, experimental: derive the record of a line that differs from the previous decoded
-                                  line only by plain bytes inside the content string, and group decode work by line shape */
 #define SSE_FLAG_KERNEL_V2 2u  /* fused producer/consumer kernel (table-driven automaton); default is the split pipeline */
 #define SSE_FLAG_COPY_OUT 8u   /* materialise every frame in the out arena. Default: a frame whose bytes already stand in the
                                   caller's input arena exactly as the reference would send them (every mode P line, and a mode R
@@ -174,7 +172,7 @@ typedef struct {
     const uint8_t        *text;     /* decoded strings */
     const sse_run        *runs;
     const sse_seg_result *segs;
-    uint32_t n_decoded, n_derived;  /* statistics: lines decoded by the automaton / derived from the previous line's parse */
+    uint32_t n_decoded, n_derived;  /* statistics: lines decoded by the automaton; n_derived is reserved (0) */
     uint32_t overflow;              /* SSE_OVF_* bits when status == SSE_ERR_OVERFLOW: which sse_config capacity to raise */
     uint32_t in_base;               /* arena offsets >= in_base refer to in[off - in_base] */
     const uint8_t *in;              /* the batch's input arena (sse_batch.in_arena), lent until sse_release like out */

@@ -8,7 +8,7 @@ from . import build as _build
 
 SSE_OK, SSE_ERR_NO_DEVICE, SSE_ERR_CUDA, SSE_ERR_ARG, SSE_ERR_BUSY, SSE_ERR_OVERFLOW, SSE_ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
 MODE_P, MODE_R, MODE_PARSE = 0, 1, 2
-FLAG_KERNEL_V1, FLAG_KERNEL_V2, FLAG_CHAINS, FLAG_COPY_OUT = 1, 2, 4, 8
+FLAG_KERNEL_V1, FLAG_KERNEL_V2, FLAG_COPY_OUT = 1, 2, 8
 NONE = 0xFFFFFFFF
 
 F_JSON_OK, F_HAS_USAGE, F_TC_NONNIL, F_TC_VALID, F_CONTENT_TEXT = 0x1, 0x2, 0x4, 0x8, 0x10

@@ -9,7 +9,7 @@
 namespace {
 
 #ifndef SSE_V1_WARPS
-#define SSE_V1_WARPS 10
+#define SSE_V1_WARPS 12
 #endif
 constexpr int WARPS_PER_CTA = SSE_V1_WARPS;
 constexpr int BUF = 8192;          // line window per warp (bytes, multiple of 16)
@@ -78,12 +78,7 @@ struct LineEnt {
     uint16_t flen;      // emitted frame length (0: nothing emitted)
     uint8_t  kind;      // K_*
     uint8_t  parse;     // 1: decode payload
-    // split pipeline: chains of lines that differ from their predecessor only by plain bytes (see chain_compare)
-    uint16_t cp, cs;    // dependent: common prefix / suffix length with the previous decoded line
-    uint16_t rel;       // index among this round's heads (chain == 0) or dependents (chain == 1)
-    uint16_t dfirst;    // head: index of its first dependent among this round's dependents
-    uint16_t ndeps;     // head: number of dependents that follow it
-    uint16_t chain;     // 0 head, 1 dependent
+    uint16_t rel;       // split pipeline: index among this round's work items
     uint16_t zc;        // 1: the frame's bytes stand in the input arena as they are (no copy; offsets are input offsets)
     uint16_t clen;      // bytes this line occupies in the out arena (frame, or the payload of a swallowed line that is decoded)
 };
@@ -91,7 +86,6 @@ enum : uint8_t { K_DROP = 0, K_EMIT = 1, K_DONE = 2, K_DONE_EXACT = 3 };
 
 struct WarpSmem {
     alignas(16) uint8_t buf[BUF + 16];
-    uint16_t spec[(BUF + 16) / 16 + 2];   // per 16-byte chunk of the window: bit i set if byte i is '"', '\\', < 0x20 or >= 0x80
     LineEnt lt[LT_MAX];
     uint16_t done_pos[DONE_MAX];
     uint32_t done_cnt;
@@ -132,89 +126,6 @@ __device__ __forceinline__ uint32_t special_mask4(uint32_t w) {
     const uint32_t q = w ^ 0x22222222u, b = w ^ 0x5C5C5C5Cu;
     return (((q - 0x01010101u) & ~q) | ((b - 0x01010101u) & ~b) | ((w - 0x20202020u) & ~w) | w) & 0x80808080u;
 }
-// exact 4-bit mask of the non-plain bytes of w ('"', '\\', < 0x20, >= 0x80)
-__device__ __forceinline__ uint32_t special_bits4(uint32_t w) {
-    const uint32_t lt = __vcmpltu4(w, 0x20202020u), q = __vcmpeq4(w, 0x22222222u), b = __vcmpeq4(w, 0x5C5C5C5Cu);
-    const uint32_t c = ((lt | q | b | w) >> 7) & 0x01010101u;
-    return ((c * 0x00204081u) >> 21) & 0xFu;
-}
-__device__ __forceinline__ uint32_t special_bits16(const uint4 &v) {
-    return special_bits4(v.x) | (special_bits4(v.y) << 4) | (special_bits4(v.z) << 8) | (special_bits4(v.w) << 12);
-}
-// 16 bytes from shared memory at an arbitrary byte offset (aligned words + funnel shifts; reads up to 3 bytes before pos)
-__device__ __forceinline__ uint4 lds16u(const uint8_t *buf, int pos) {
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(buf + (pos & ~3));
-    const uint32_t sh = (uint32_t)(pos & 3) * 8u;
-    const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4];
-    uint4 v;
-    v.x = __funnelshift_r(a0, a1, sh); v.y = __funnelshift_r(a1, a2, sh); v.z = __funnelshift_r(a2, a3, sh); v.w = __funnelshift_r(a3, a4, sh);
-    return v;
-}
-__device__ __forceinline__ int first_diff16(const uint4 &x, const uint4 &y) {     // index of the first differing byte, 16 if none
-    uint32_t d;
-    if ((d = x.x ^ y.x) != 0) return (__ffs((int)d) - 1) >> 3;
-    if ((d = x.y ^ y.y) != 0) return 4 + ((__ffs((int)d) - 1) >> 3);
-    if ((d = x.z ^ y.z) != 0) return 8 + ((__ffs((int)d) - 1) >> 3);
-    if ((d = x.w ^ y.w) != 0) return 12 + ((__ffs((int)d) - 1) >> 3);
-    return 16;
-}
-__device__ __forceinline__ int equal_tail16(const uint4 &x, const uint4 &y) {     // number of equal bytes counted from the end
-    uint32_t d;
-    if ((d = x.w ^ y.w) != 0) return __clz((int)d) >> 3;
-    if ((d = x.z ^ y.z) != 0) return 4 + (__clz((int)d) >> 3);
-    if ((d = x.y ^ y.y) != 0) return 8 + (__clz((int)d) >> 3);
-    if ((d = x.x ^ y.x) != 0) return 12 + (__clz((int)d) >> 3);
-    return 16;
-}
-// true if window bytes [x0, x1) are all plain according to the per-chunk bitmap (warp-cooperative)
-__device__ __forceinline__ bool region_plain(const uint16_t *spec, int x0, int x1) {
-    bool bad = false;
-    if (x1 > x0) {
-        const int c0 = x0 >> 4, c1 = (x1 - 1) >> 4;
-        for (int c = c0 + (int)(threadIdx.x & 31u); c <= c1; c += 32) {
-            uint32_t bits = spec[c];
-            if (c == c0) bits &= 0xFFFFu << (x0 & 15);
-            if (c == c1) bits &= 0xFFFFu >> (15 - ((x1 - 1) & 15));
-            bad |= bits != 0;
-        }
-    }
-    return !__any_sync(0xFFFFFFFFu, bad);
-}
-// Warp-cooperative comparison of two payloads of the window: A = buf[a, a+la), B = buf[b, b+lb) (B is the previous decoded line).
-// Returns true when A differs from B only inside a region where both hold plain string bytes (no '"', '\\', control,
-// non-ASCII): cp = common prefix, cs = common suffix (cp + cs <= min(la, lb)). Then A's json.Unmarshal result equals B's with
-// one string value replaced -- which string is checked by the decode kernel once B is parsed.
-__device__ __noinline__ bool chain_compare(const uint8_t *buf, const uint16_t *spec, int a, int la, int b, int lb, int &cp, int &cs) {
-    const int lane = (int)(threadIdx.x & 31u);
-    const int m = min(la, lb);
-    if (m < 32 || a + la - 16 < 4 || b + lb - 16 < 4) return false;
-    cp = m;
-    for (int off = 0; off < m; off += 512) {
-        const int o = off + lane * 16;
-        int idx = 16;
-        if (o < m) {
-            idx = first_diff16(lds16u(buf, a + o), lds16u(buf, b + o));
-            if (idx >= min(16, m - o)) idx = 16;
-        }
-        const unsigned ball = __ballot_sync(0xFFFFFFFFu, idx < 16);
-        if (ball) { const int l = __ffs((int)ball) - 1; cp = off + l * 16 + __shfl_sync(0xFFFFFFFFu, idx, l); break; }
-    }
-    const int lim = m - cp;
-    cs = lim;
-    for (int off = 0; off < lim; off += 512) {
-        const int o = off + lane * 16;       // bytes already covered, counted from the end
-        int eq = 16; bool mis = false;
-        if (o < lim) {
-            eq = equal_tail16(lds16u(buf, a + la - o - 16), lds16u(buf, b + lb - o - 16));
-            const int valid = min(16, lim - o);
-            if (eq >= valid) eq = valid; else mis = true;
-        }
-        const unsigned ball = __ballot_sync(0xFFFFFFFFu, mis);
-        if (ball) { const int l = __ffs((int)ball) - 1; cs = off + l * 16 + __shfl_sync(0xFFFFFFFFu, eq, l); break; }
-    }
-    return region_plain(spec, a + cp, a + la - cs) && region_plain(spec, b + cp, b + lb - cs);
-}
-
 // ---------------------------------------------------------------- strings.TrimSpace pieces
 // unicode.IsSpace code points in UTF-8: ASCII \t\n\v\f\r ' ', U+0085, U+00A0, U+1680, U+2000-200A,
 // U+2028, U+2029, U+202F, U+205F, U+3000 (Go strings.TrimSpace / utf8.DecodeRune semantics).

@@ -37,8 +37,7 @@ struct Counters {
     int32_t  status;
     uint32_t n_items;      // split pipeline: work items written by the produce kernel
     uint32_t item_ticket;  // split pipeline: next item batch for the decode kernel
-    uint32_t n_deps;       // split pipeline: dependent lines (candidates for derivation from the previous line's parse)
-    uint32_t n_dep_decoded;// ... of which the decode kernel had to decode after all
+    uint32_t reserved0, reserved1;
     uint32_t overflow;     // SSE_OVF_* bits: which arena was too small
     uint32_t pad[2];
     // device-only tail (the host reads the struct up to here)
@@ -68,10 +67,8 @@ struct KParams {
     // split pipeline (produce -> decode -> finalize)
     uint4 *items;            uint32_t cap_items;   // src, len | rmode << 31, rec, seg
     uint32_t *seg_term;                            // per segment: smallest terminating record index, SSE_NONE if none
-    uint2 *item_deps;                              // per item: first dependent, count
     uint32_t flags;                                // sse_config.flags
-    uint4 *items_sorted; uint2 *item_deps_sorted;  // items grouped by shape class so that the 32 lanes of a decode batch walk alike lines
-    uint4 *deps;             uint32_t cap_deps;    // src, len, rec, cp | cs << 16 (common prefix / suffix with the previous line)
+    uint4 *items_sorted;                           // items ordered by (length bucket, shape class): the 32 lanes of a decode batch walk alike lines
 };
 
 #ifdef __CUDACC__

@@ -43,7 +43,7 @@ struct Slot {
     sse_usage *d_usages = nullptr; uint8_t *d_text = nullptr; sse_run *d_runs = nullptr; sse_seg_result *d_segres = nullptr;
     Counters *d_ctr = nullptr;
     uint4 *d_items = nullptr; uint32_t *d_segterm = nullptr;   // split pipeline scratch (device only)
-    uint2 *d_itemdeps = nullptr; uint4 *d_deps = nullptr; uint4 *d_items2 = nullptr; uint2 *d_itemdeps2 = nullptr;
+    uint4 *d_items2 = nullptr;                                 // items ordered for the decode kernel
     uint32_t n_segs = 0, in_bytes = 0;
 };
 
@@ -79,7 +79,7 @@ void free_slot(Slot &s) {
     cudaFreeHost(s.h_ctr);
     cudaFree(s.d_segs); cudaFree(s.d_out);   // d_in lives inside d_out's allocation
     cudaFree(s.d_frames); cudaFree(s.d_recs); cudaFree(s.d_tcs);
-    cudaFree(s.d_usages); cudaFree(s.d_text); cudaFree(s.d_runs); cudaFree(s.d_segres); cudaFree(s.d_ctr); cudaFree(s.d_items); cudaFree(s.d_segterm); cudaFree(s.d_itemdeps); cudaFree(s.d_deps); cudaFree(s.d_items2); cudaFree(s.d_itemdeps2);
+    cudaFree(s.d_usages); cudaFree(s.d_text); cudaFree(s.d_runs); cudaFree(s.d_segres); cudaFree(s.d_ctr); cudaFree(s.d_items); cudaFree(s.d_segterm); cudaFree(s.d_items2);
 }
 
 KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
@@ -95,8 +95,7 @@ KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
     p.runs = s.d_runs; p.cap_runs = c->cfg.max_runs;
     p.seg_results = s.d_segres; p.ctr = s.d_ctr;
     p.items = s.d_items; p.cap_items = c->cfg.max_recs; p.seg_term = s.d_segterm;
-    p.item_deps = s.d_itemdeps; p.deps = s.d_deps; p.cap_deps = c->cfg.max_recs;
-    p.items_sorted = s.d_items2; p.item_deps_sorted = s.d_itemdeps2; p.flags = c->cfg.flags;
+    p.items_sorted = s.d_items2; p.flags = c->cfg.flags;
     return p;
 }
 
@@ -148,7 +147,7 @@ int do_download(sse_ctx *c, Slot &s, sse_result *res, cudaStream_t st) {
     }
     res->n_frames = k.n_frames; res->n_recs = k.n_recs; res->n_tcs = k.n_tcs; res->n_usages = k.n_usages;
     res->n_runs = k.n_runs; res->out_bytes = k.out_bytes; res->text_bytes = k.text_bytes;
-    res->n_decoded = k.n_items + k.n_dep_decoded; res->n_derived = k.n_deps - k.n_dep_decoded;
+    res->n_decoded = k.n_items; res->n_derived = 0;
     if (k.out_bytes) CU(cudaMemcpyAsync(s.h_out, s.d_out, k.out_bytes, cudaMemcpyDeviceToHost, st));
     if (k.n_frames) CU(cudaMemcpyAsync(s.h_frames, s.d_frames, (size_t)k.n_frames * sizeof(sse_frame), cudaMemcpyDeviceToHost, st));
     if (k.n_recs) CU(cudaMemcpyAsync(s.h_recs, s.d_recs, (size_t)k.n_recs * sizeof(sse_rec), cudaMemcpyDeviceToHost, st));
@@ -249,8 +248,7 @@ int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
         ok = ok && dalloc(s.d_tcs, cfg->max_tcs) && dalloc(s.d_usages, cfg->max_usages) && dalloc(s.d_text, cfg->text_arena_bytes);
         ok = ok && dalloc(s.d_runs, cfg->max_runs) && dalloc(s.d_segres, cfg->max_segs) && dalloc(s.d_ctr, 1);
         ok = ok && dalloc(s.d_items, cfg->max_recs) && dalloc(s.d_segterm, cfg->max_segs);
-        ok = ok && dalloc(s.d_itemdeps, cfg->max_recs) && dalloc(s.d_deps, cfg->max_recs);
-        ok = ok && dalloc(s.d_items2, cfg->max_recs) && dalloc(s.d_itemdeps2, cfg->max_recs);
+        ok = ok && dalloc(s.d_items2, cfg->max_recs);
     }
     if (!ok) { sse_destroy(c); return SSE_ERR_CUDA; }
     *out = c;

@@ -143,7 +143,6 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                         uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
                         nlm = eqmask16(v, 0x0A0A0A0Au);
                         if (mode & SSE_MODE_R) brm = done_candidates16(v);
-                        if (SPLIT && (mode & SSE_MODE_PARSE) && (P.flags & SSE_FLAG_CHAINS)) W.spec[off >> 4] = (uint16_t)special_bits16(v);
                         // mask bytes outside [pos, fill)
                         uint32_t valid = 0xFFFFu;
                         if (off < pos) valid &= 0xFFFFu << (pos - off);
@@ -233,11 +232,9 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                     pre_b[h] = tot_b + sb - vb; pre_f[h] = tot_f + sf - vf; pre_r[h] = tot_r + sr - vr;
                     tot_b += __shfl_sync(FULL, sb, 31); tot_f += __shfl_sync(FULL, sf, 31); tot_r += __shfl_sync(FULL, sr, 31);
                 }
-                // split pipeline: chains. A line that differs from the previous decoded line of this round only by plain
-                // string bytes becomes a dependent of it (its record is derived by the decode kernel, not re-decoded).
-                uint32_t tot_q = 0, tot_d = 0, qb = 0, db = 0;
-                if (SPLIT && !(P.flags & SSE_FLAG_CHAINS)) {
-                    // every decoded line is its own work item: index = rank among this round's emitted data lines
+                // split pipeline: every line to decode is a work item; index = rank among this round's items
+                uint32_t tot_q = 0, qb = 0;
+                if (SPLIT) {
                     uint32_t my_q = 0;
                     #pragma unroll
                     for (int h = 0; h < 2; h++) my_q += (my_parse[h] && (my_kind[h] == K_EMIT || my_kind[h] == K_DONE)) ? 1u : 0u;
@@ -249,48 +246,21 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                     #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         int i = (int)lane + 32 * h;
-                        if (i < n_lines && my_parse[h] && (my_kind[h] == K_EMIT || my_kind[h] == K_DONE)) {
-                            LineEnt &w = W.lt[i];
-                            w.chain = 0; w.rel = (uint16_t)(pre_q + ((h == 1 && my_parse[0] && (my_kind[0] == K_EMIT || my_kind[0] == K_DONE)) ? 1u : 0u)); w.dfirst = 0; w.ndeps = 0;
-                        }
+                        if (i < n_lines && my_parse[h] && (my_kind[h] == K_EMIT || my_kind[h] == K_DONE))
+                            W.lt[i].rel = (uint16_t)(pre_q + ((h == 1 && my_parse[0] && (my_kind[0] == K_EMIT || my_kind[0] == K_DONE)) ? 1u : 0u));
                     }
-                    __syncwarp();
-                } else if (SPLIT) {
-                    int prev = -1, cur_head = -1;
-                    uint32_t cur_deps = 0;
-                    for (int i = 0; i < n_lines; i++) {
-                        const LineEnt e = W.lt[i];
-                        if (!(e.parse && (e.kind == K_EMIT || e.kind == K_DONE))) continue;
-                        bool dep = false; int cp = 0, cs = 0;
-                        if (prev >= 0 && e.kind == K_EMIT) {   // a swallowed line is always a head and never a template
-                            const LineEnt pe = W.lt[prev];
-                            dep = chain_compare(buf, W.spec, e.pay_s, e.pay_e - e.pay_s, pe.pay_s, pe.pay_e - pe.pay_s, cp, cs);
-                        }
-                        if (lane == 0) {
-                            LineEnt &w = W.lt[i];
-                            if (dep) { w.chain = 1; w.cp = (uint16_t)cp; w.cs = (uint16_t)cs; w.rel = (uint16_t)tot_d; }
-                            else {
-                                if (cur_head >= 0) W.lt[cur_head].ndeps = (uint16_t)cur_deps;
-                                w.chain = 0; w.rel = (uint16_t)tot_q; w.dfirst = (uint16_t)tot_d; w.ndeps = 0;
-                            }
-                        }
-                        if (dep) { tot_d++; cur_deps++; } else { tot_q++; cur_head = i; cur_deps = 0; }
-                        prev = (e.kind == K_EMIT) ? i : -1;
-                    }
-                    if (lane == 0 && cur_head >= 0) W.lt[cur_head].ndeps = (uint16_t)cur_deps;
                     __syncwarp();
                 }
                 uint32_t ob = 0, fb = 0, rb = 0;
                 if (lane == 0) {
                     if (SPLIT && tot_q) qb = atomicAdd(&P.ctr->n_items, tot_q);
-                    if (SPLIT && tot_d) db = atomicAdd(&P.ctr->n_deps, tot_d);
                     if (tot_b) ob = atomicAdd(&P.ctr->out_bytes, (tot_b + 15u) & ~15u);
                     if (tot_f) fb = atomicAdd(&P.ctr->n_frames, tot_f);
                     if (tot_r) rb = atomicAdd(&P.ctr->n_recs, tot_r);
                 }
-                ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0); qb = __shfl_sync(FULL, qb, 0); db = __shfl_sync(FULL, db, 0);
+                ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0); qb = __shfl_sync(FULL, qb, 0);
                 if (ob + tot_b + 16 > P.cap_out || fb + tot_f > P.cap_frames || rb + tot_r > P.cap_recs ||
-                    (SPLIT && (qb + tot_q > P.cap_items || db + tot_d > P.cap_deps))) {
+                    (SPLIT && qb + tot_q > P.cap_items)) {
                     if (lane == 0) sse_overflow(P.ctr, SSE_OVF_OUT);
                     overflow = true; break;
                 }
@@ -341,20 +311,14 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                             uint4 it;
                             it.x = (uint32_t)(cx.out_delta + (int64_t)e.pay_s);
                             it.z = rb + pre_r[h];
-                            if (e.chain == 0) {
-                                // shape class; the second decoded line of a round (first content delta, the longest) sorts first: long work early
-                                const uint32_t ord = min((uint32_t)e.rel, 7u);
-                                const uint32_t cls = ((ord == 1u ? 0u : (ord == 0u ? 1u : ord)) << 2) | (seg.provider & 3u);
-                                // bit 31: the line can terminate the stream (emitted, mode R); bit 30: swallowed line (SSE_F_DONE_LINE)
-                                it.y = (uint32_t)(e.pay_e - e.pay_s) | (cls << 24) | (swallowed ? 0x40000000u : ((mode & SSE_MODE_R) ? 0x80000000u : 0u));
-                                it.w = s;
-                                P.items[qb + e.rel] = it;
-                                if (P.flags & SSE_FLAG_CHAINS) P.item_deps[qb + e.rel] = make_uint2(db + e.dfirst, e.ndeps);
-                            } else {
-                                it.y = (uint32_t)(e.pay_e - e.pay_s);
-                                it.w = (uint32_t)e.cp | ((uint32_t)e.cs << 16);
-                                P.deps[db + e.rel] = it;
-                            }
+                            // scheduling key of the decode kernel's item sort: provider hint x position of the line in its round; the
+                            // second decoded line of a round (first content delta, the longest) sorts first: long work early
+                            const uint32_t ord = min((uint32_t)e.rel, 7u);
+                            const uint32_t cls = ((ord == 1u ? 0u : (ord == 0u ? 1u : ord)) << 2) | (seg.provider & 3u);
+                            // bit 31: the line can terminate the stream (emitted, mode R); bit 30: swallowed line (SSE_F_DONE_LINE)
+                            it.y = (uint32_t)(e.pay_e - e.pay_s) | (cls << 24) | (swallowed ? 0x40000000u : ((mode & SSE_MODE_R) ? 0x80000000u : 0u));
+                            it.w = s;
+                            P.items[qb + e.rel] = it;
                             continue;
                         }
                         ParseOut po;

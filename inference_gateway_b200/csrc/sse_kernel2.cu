@@ -51,12 +51,6 @@ struct LaneScratch {               // cold per-lane state (usage ints, the tool-
     uint32_t tc_flags, tc_dec;
     uint32_t id_off, id_len, type_off, type_len, name_off, name_len, args_off, args_len;
 };
-// Template of the last decoded line of a chain (split pipeline): what a dependent line's record is derived from.
-struct LaneTpl {
-    sse_rec rec;
-    uint32_t ok, vs, ve, len, run_cp, run_cs, pad0, pad1;   // content span [vs, ve) relative to the payload start
-};
-
 struct WarpSmem2 {
     alignas(16) uint8_t buf[V2_BUF + 16];
     LineEnt lt[LT_MAX];
@@ -87,7 +81,6 @@ struct Lane {
     unsigned long long ct, ct1, sstk;   // container-type bit stack (1 = array), 128 levels
     uint32_t content_off, content_len, tc_count, tc_first, tc_prev;
     uint32_t rec, frame, slot, plen;
-    uint32_t dep_first, dep_cnt;       // split pipeline: dependents of the line being decoded
     bool busy;
 };
 
@@ -320,7 +313,7 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
 }
 
 // A line retires: final syntax check, record, termination bookkeeping (agent.go:205-242).
-__device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J, LaneTpl *tp = nullptr) {
+__device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
     bool terminates = false;
     if (!(L.sf & SF_SYN)) {
         if (L.depth == 0 && (L.st == S_NZERO || L.st == S_NINT || L.st == S_NFRAC || L.st == S_NEXP)) {
@@ -362,14 +355,6 @@ __device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJo
     }
     r.payload_len = L.plen;
     P.recs[L.rec] = r;
-    if (tp) {
-        // a line is a usable template when its only captured value is an unescaped content string
-        tp->ok = (r.flags & SSE_F_JSON_OK) && L.n_choices > 0 && (L.sf & SF_CSET) && !(L.sf & (SF_CDEC | SF_CBAD | SF_TCNONNIL | SF_USAGE)) &&
-                 L.tc_count == 0 && !terminates;
-        tp->rec = r;
-        tp->vs = L.content_off - (L.pe - L.plen); tp->ve = tp->vs + L.content_len; tp->len = L.plen;
-        tp->run_cp = tp->run_cs = 0xFFFFFFFFu;
-    }
     L.busy = false;
     return terminates;
 }
@@ -499,7 +484,7 @@ sse_stream_kernel_v2(const __grid_constant__ KParams P, const DfaTables *__restr
     Lane L; L.busy = false; L.p = L.pe = 0; L.win = make_uint4(0, 0, 0, 0);
     L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.km = TRIE_ROOT; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
     L.finish = 0; L.ct = L.ct1 = L.sstk = 0; L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
-    L.rec = L.frame = L.slot = L.plen = 0; L.dep_first = L.dep_cnt = 0;
+    L.rec = L.frame = L.slot = L.plen = 0;
 
     Producer pr; pr.phase = 0; pr.more = true;
     uint32_t head = 0, tail = 0;     // ring indices (warp-uniform registers mirror of W.ring_*)
@@ -855,10 +840,8 @@ struct CtaSmem3 {
     DfaTables T;
     LaneScratch ls[V3_WARPS * 32];
     LaneJobs jobs[V3_WARPS * 32];
-    LaneTpl tpl[1];                 // V3_WARPS * 32 entries with SSE_FLAG_CHAINS (the launch sizes the dynamic part), else unused
 };
-constexpr size_t decode_smem_bytes(bool chains) { return sizeof(CtaSmem3) + (chains ? sizeof(LaneTpl) * (V3_WARPS * 32 - 1) : 0); }
-static_assert(decode_smem_bytes(true) <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(CtaSmem3) <= 227 * 1024, "shared memory budget");
 
 __global__ void __launch_bounds__(V3_WARPS * 32, 1)
 sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict__ gT) {
@@ -873,17 +856,15 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
     const DfaTables &T = cs.T;
     LaneScratch &S = cs.ls[threadIdx.x];
     LaneJobs *J = &cs.jobs[threadIdx.x];
-    LaneTpl &Tp = cs.tpl[(P.flags & SSE_FLAG_CHAINS) ? threadIdx.x : 0];   // only touched with CHAINS
     LaneJobs *Jw = &cs.jobs[threadIdx.x & ~31u];   // this warp's 32 queues
     J->n = 0;
     const uint32_t lane = lane_id();
     const uint32_t n_items = min(P.ctr->n_items, P.cap_items);
-    const bool chains = (P.flags & SSE_FLAG_CHAINS) != 0;
 
     Lane L; L.busy = false; L.p = L.pe = 0; L.win = make_uint4(0, 0, 0, 0);
     L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.km = TRIE_ROOT; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
     L.finish = 0; L.ct = L.ct1 = L.sstk = 0; L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
-    L.rec = L.frame = L.slot = L.plen = 0; L.dep_first = L.dep_cnt = 0;
+    L.rec = L.frame = L.slot = L.plen = 0;
 
     for (;;) {
         uint32_t base = 0;
@@ -892,60 +873,25 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
         if (base >= n_items) break;
         const uint32_t idx = base + lane;
         if (idx < n_items) {
-            const bool sorted = chains;
             const uint4 it = P.items_sorted[idx];
             L.p = it.x; L.plen = it.y & 0x00FFFFFFu; L.pe = it.x + L.plen; L.rec = it.z; L.slot = it.w;   // slot: segment index
             L.frame = P.recs[it.z].frame;
-            L.dep_first = L.dep_cnt = 0;
-            if (sorted) { const uint2 dd = P.item_deps_sorted[idx]; L.dep_first = dd.x; L.dep_cnt = dd.y; if (dd.y) prefetch_l2(reinterpret_cast<const uint8_t *>(&P.deps[dd.x])); }
+           
             L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.km = TRIE_ROOT; L.slen = 0;
             L.sf = ((it.y & 0x80000000u) ? SF_RMODE : 0u) | ((it.y & 0x40000000u) ? SF_DONELINE : 0u);
             L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
             L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
             S.u_prompt = S.u_completion = S.u_total = 0;
             L.busy = true;
-            if (L.p < L.pe) {
-                L.win = ldwin16<true>(P.out, L.p);
-                // items are grouped by shape, not by address: pull the rest of the payload towards L2 ahead of the automaton
-                if (sorted) for (uint32_t q = (L.p & ~127u) + 128u; q < L.pe && q < L.p + 1024u; q += 128u) prefetch_l2(P.out + q);
-            }
+            if (L.p < L.pe) L.win = ldwin16<true>(P.out, L.p);
         }
         while (__any_sync(FULL, L.busy)) {
             #pragma unroll 1
             for (int round = 0; round < ROUNDS; round++) {
                 v2_round<true>(P, T, L, S, J);
                 if (L.busy && L.p >= L.pe) {
-                    if (v2_finish_line(P, L, S, J, chains ? &Tp : nullptr)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
+                    if (v2_finish_line(P, L, S, J)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
                     L.p = L.pe = 0;
-                    // dependents: lines that differ from their predecessor only by plain string bytes (chain_compare). If the
-                    // difference lies inside the template's content string, the record is the template's with the content span
-                    // moved; otherwise the line is decoded and becomes the template for the rest of the chain.
-                    while (L.dep_cnt) {
-                        const uint4 d = P.deps[L.dep_first];
-                        L.dep_first++; L.dep_cnt--;
-                        Tp.run_cp = min(Tp.run_cp, d.w & 0xFFFFu); Tp.run_cs = min(Tp.run_cs, d.w >> 16);
-                        if (Tp.ok && Tp.run_cp >= Tp.vs && Tp.len - Tp.run_cs <= Tp.ve) {
-                            // the stub already holds the frame index: write the other 28 bytes without reading it back
-                            sse_rec r = Tp.rec;
-                            r.content_off = d.x + Tp.vs; r.content_len = d.y - Tp.len + (Tp.ve - Tp.vs);
-                            r.payload_len = d.y;
-                            uint32_t *dst = reinterpret_cast<uint32_t *>(&P.recs[d.z]);
-                            dst[1] = r.flags;
-                            *reinterpret_cast<uint2 *>(dst + 2) = make_uint2(r.content_off, r.content_len);
-                            *reinterpret_cast<uint4 *>(dst + 4) = make_uint4(r.tc_first, (uint32_t)r.tc_count | ((uint32_t)r.n_choices << 16), r.usage, r.payload_len);
-                        } else {
-                            atomicAdd(&P.ctr->n_dep_decoded, 1u);
-                            L.p = d.x; L.plen = d.y; L.pe = d.x + d.y; L.rec = d.z; L.frame = P.recs[d.z].frame;
-                            L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.km = TRIE_ROOT; L.slen = 0;
-                            L.sf &= SF_RMODE;
-                            L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
-                            L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
-                            S.u_prompt = S.u_completion = S.u_total = 0;
-                            L.busy = true;
-                            if (L.p < L.pe) L.win = ldwin16<true>(P.out, L.p);
-                            break;
-                        }
-                    }
                 }
             }
             // strings that need unquoting were queued by the lanes: decode them with the whole warp
@@ -972,12 +918,11 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
 // ---------------------------------------------------------------- split pipeline, stage 1b: order the work items
 // A decode warp takes 32 items and runs until the longest of them is done, so a batch of mixed lengths idles most lanes
 // (payloads are lognormal 96..4096 B: in arrival order a batch is 34 % busy). Counting sort by payload length / 64, longest
-// bucket first: batches are then 94 % busy and the long lines do not land on the tail of the kernel. With SSE_FLAG_CHAINS the
-// key is the shape class instead (provider x position of the line in its round), which the chain templates need.
+// bucket first, and within a length bucket by shape class (provider hint x position of the line in its round): batches are then
+// 94 % busy, their lanes stop at the same actions, and the long lines do not land on the tail of the kernel.
 constexpr int N_BUCKETS = SSE_N_BUCKETS;
 __device__ __forceinline__ uint32_t item_bucket(const KParams &P, uint32_t y) {
     const uint32_t cls = (y >> 24) & 31u;
-    if (P.flags & SSE_FLAG_CHAINS) return cls;
     return (((uint32_t)SSE_LEN_BUCKETS - 1u - min((y & 0x00FFFFFFu) >> SSE_LEN_SHIFT, (uint32_t)SSE_LEN_BUCKETS - 1u)) << 5) | cls;
 }
 __global__ void sse_bucket_hist_kernel(const KParams P) {
@@ -1017,7 +962,6 @@ constexpr int SCATTER_TPB = 256, SCATTER_IPT = 8;   // one block places 2048 con
 __global__ void __launch_bounds__(SCATTER_TPB) sse_bucket_scatter_kernel(const KParams P) {
     __shared__ uint32_t h[N_BUCKETS], base[N_BUCKETS];
     const uint32_t n = min(P.ctr->n_items, P.cap_items);
-    const bool chains = (P.flags & SSE_FLAG_CHAINS) != 0;
     for (uint32_t blk = blockIdx.x * (SCATTER_TPB * SCATTER_IPT); blk < n; blk += gridDim.x * (SCATTER_TPB * SCATTER_IPT)) {
         for (int b = threadIdx.x; b < N_BUCKETS; b += SCATTER_TPB) h[b] = 0;
         __syncthreads();
@@ -1036,7 +980,6 @@ __global__ void __launch_bounds__(SCATTER_TPB) sse_bucket_scatter_kernel(const K
             if (i < n) {
                 const uint32_t pos = base[item_bucket(P, it[k].y)] + rank[k];
                 P.items_sorted[pos] = it[k];
-                if (chains) P.item_deps_sorted[pos] = P.item_deps[i];
             }
         }
         __syncthreads();
@@ -1100,7 +1043,7 @@ int sse_v2_prepare(int device) {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(sse_stream_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem2));
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(sse_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem_bytes(true));
+    e = cudaFuncSetAttribute(sse_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
     if (e != cudaSuccess) return (int)e;
     g_tables_dev[device] = d;
     return 0;
@@ -1118,7 +1061,7 @@ int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int
     sse_bucket_hist_kernel<<<sm_count * 2, 512, 0, (cudaStream_t)stream>>>(p);
     sse_bucket_scan_kernel<<<1, SCAN_TPB, 0, (cudaStream_t)stream>>>(p);
     sse_bucket_scatter_kernel<<<sm_count * 2, SCATTER_TPB, 0, (cudaStream_t)stream>>>(p);
-    sse_decode_kernel<<<sm_count, V3_WARPS * 32, decode_smem_bytes((p.flags & SSE_FLAG_CHAINS) != 0), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
+    sse_decode_kernel<<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const int tpb = 256;
