@@ -832,7 +832,7 @@ sse_stream_kernel_v2(const __grid_constant__ KParams P, const DfaTables *__restr
 // near-identical structure in lockstep); no producer code and no line window in this kernel: small instruction
 // footprint, shared memory only for the tables and the cold per-lane state.
 #ifndef SSE_V3_WARPS
-#define SSE_V3_WARPS 28
+#define SSE_V3_WARPS 32
 #endif
 constexpr int V3_WARPS = SSE_V3_WARPS;
 
