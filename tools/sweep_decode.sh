@@ -1,4 +1,7 @@
-for cfg in "-DSSE_V3_WARPS=28" "-DSSE_V3_WARPS=30" "-DSSE_V3_WARPS=32" "-DSSE_V3_WARPS=24" "-DSSE_KSTEPS=3" "-DSSE_SKIPW=6" "-DSSE_LEN_SHIFT=4"; do
-  SSE_NVCC_DEFS="$cfg" python inference_gateway_b200/build.py --force > /dev/null 2>&1 || echo "build failed $cfg"
-  timeout 200 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$cfg', d['ms_per_step'])"
-done
+python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+python bench.py --steps 50 --warmup 3 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; tail -c 200 gpurun_out/bench_1gpu.json
+python bench.py --steps 50 --warmup 3 --mode 0 --no-cpu-baseline > gpurun_out/bench_1gpu_modeP.json 2>/dev/null
+python tools/latency_bench.py > gpurun_out/latency.json 2> gpurun_out/latency.err
+python tools/tick_bench.py 2>/dev/null | tail -1 > gpurun_out/tick.json; cat gpurun_out/tick.json
+python -c "import __graft_entry__ as g; g.smoke()"
+bash tools/profile_round.sh > /dev/null 2>&1
