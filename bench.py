@@ -240,7 +240,7 @@ def main():
     # nvidia-smi needs a few hundred ms before its first sample: keep the GPU under the same load (untimed) meanwhile,
     # so that the clock samples bracket the timed region and are all taken under load
     t_pre = time.perf_counter()
-    while time.perf_counter() - t_pre < 0.6:
+    while time.perf_counter() - t_pre < 1.2:
         step()
         torch.cuda.synchronize()
     if world > 1:

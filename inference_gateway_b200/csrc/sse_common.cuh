@@ -437,7 +437,7 @@ __device__ __noinline__ uint32_t classify_finish(const uint8_t *s, int n) {
 // Deferred unquote jobs of one lane: drained warp-cooperatively (warp_unquote) instead of byte-by-byte on one lane.
 struct UnquoteJob { uint32_t s, e, dst, pad; uint32_t *patch; };
 #ifndef SSE_MAX_JOBS
-#define SSE_MAX_JOBS 2
+#define SSE_MAX_JOBS 1
 #endif
 constexpr int MAX_JOBS = SSE_MAX_JOBS;   // queue full: the lane unquotes the string itself (slow, exact)
 struct LaneJobs { uint32_t n; uint32_t pad; UnquoteJob j[MAX_JOBS]; };

@@ -26,7 +26,7 @@ constexpr int V2_BUF = 6144;       // line window per warp
 constexpr int RING = 128;          // work items per warp
 constexpr int SEGSLOTS = 8;        // segments in flight per warp
 #ifndef SSE_ROUNDS
-#define SSE_ROUNDS 4
+#define SSE_ROUNDS 2
 #endif
 #ifndef SSE_KSTEPS
 #define SSE_KSTEPS 2
