@@ -1,15 +1,18 @@
-// sse_kernel.cu -- the streaming-response hot path on sm_100a.
+// sse_kernel.cu -- stage 1 of the default pipeline (produce), and the fused first-generation kernel.
 //
-// One persistent warp per connection segment (dynamic ticket), everything for that segment in one pass:
-//   stage   carry tail (HBM, per connection) + new segment bytes -> warp-private shared-memory window
-//   split   SWAR/ballot newline scan -> line table            (provider.go:322 ReadBytes('\n'))
+// One persistent warp per connection segment (dynamic ticket):
+//   stage    carry tail (HBM, per connection) + new segment bytes -> warp-private shared-memory window
+//   split    SWAR/ballot newline scan -> line table            (provider.go:322 ReadBytes('\n'))
 //   classify strings.TrimSpace / Contains "[DONE]" / HasPrefix "data: "   (agent.go:178-193), or verbatim (mode P)
-//   emit    warp-cooperative serializer: frame bytes -> out arena           (agent.go:195 / routes.go:613)
-//   decode  one lane per line: single-pass JSON validator + typed field extractor that reproduces
-//           json.Unmarshal into CreateChatCompletionStreamResponse         (agent.go:199-242)
-//   finish  early termination (agent.go:235-242), carry update, per-segment result
+//   emit     frame table; a frame that stands in the input arena as it must be sent is a span of it (zero-copy), the others
+//            go through the warp-cooperative serializer into the out arena      (agent.go:195 / routes.go:613)
+//   SPLIT = true  (default pipeline): a stub record + a 16-byte work item per line to decode; sse_kernel2.cu sorts the
+//                 items, decodes them (sse_decode_kernel) and resolves early termination (sse_finalize_kernel)
+//   SPLIT = false (SSE_FLAG_KERNEL_V1): one lane per line runs the sequential decoder decode_chunk right here, then
+//                 early termination (agent.go:235-242); an independent second implementation kept for the tests
+//   finish   carry update, per-segment result
 //
-// Pure integer/byte work; HBM-bound by design (bytes are read once into shared memory and written once).
+// Pure integer/byte work, no tensor cores.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "sse_common.cuh"
@@ -17,8 +20,7 @@
 namespace {
 
 // ---------------------------------------------------------------- the kernel
-// SPLIT = false: the complete v1 kernel. SPLIT = true: stage 1 of the split pipeline (stage, split, classify, emit;
-// one work item per emitted data line goes to P.items for sse_decode_kernel; no early termination here).
+// SPLIT = false: the complete v1 kernel. SPLIT = true: stage 1 of the split pipeline (no JSON decoder in this instantiation).
 #ifndef SSE_V1_MINB
 #define SSE_V1_MINB 2
 #endif

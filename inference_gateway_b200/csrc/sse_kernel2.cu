@@ -1,17 +1,16 @@
-// sse_kernel2.cu -- v2 of the streaming-response kernel for sm_100a.
+// sse_kernel2.cu -- stages 2-4 of the default pipeline (work-item sort, decode, finalize), and the fused v2 kernel.
 //
-// Every warp is an autonomous producer/consumer pipeline (no CTA-wide barriers after start-up):
-//   produce (warp-cooperative, one segment at a time, same semantics as v1):
-//       stage carry + segment -> shared window, SWAR/ballot line split, classify (TrimSpace / [DONE] / "data: "),
-//       bump-allocate, warp-cooperative serializer -> out arena, push one work item per emitted data line
-//   consume (one lane per line, all 32 lanes busy, uniform control flow):
-//       a table-driven pushdown automaton steps one byte per iteration per lane, reading the frame it decodes
-//       straight from the out arena (L2-resident, 16-byte register window per lane). Syntax, type compatibility
-//       and field capture follow json.Unmarshal into CreateChatCompletionStreamResponse; keys are matched by a
-//       case-folding trie walked alongside; rare cases (escaped keys, int/float range checks, string unquoting)
-//       fall to the sequential helpers of sse_common.cuh.
-//   Early termination (agent.go:235-242) is resolved when the last line of a segment retires: the segment's runs
-//   are cut after the terminating chunk and the connection is marked finished.
+// The table-driven automaton (v2_round / v2_action / v2_finish_line): one lane per line steps a pushdown automaton over the
+// payload it reads through a 16-byte register window. Syntax, type compatibility and field capture follow json.Unmarshal into
+// CreateChatCompletionStreamResponse; keys are matched by a case-folding trie walked alongside; rare cases (escaped keys,
+// int/float range checks) fall to the sequential helpers of sse_common.cuh; strings that need unquoting are queued and decoded
+// by the whole warp.
+//
+//   sse_bucket_{hist,scan,scatter}_kernel  counting sort of the produce stage's work items by (length, shape class)
+//   sse_decode_kernel                      persistent, one CTA per SM: warps pull 32 sorted items and run the automaton
+//   sse_finalize_kernel                    early termination (agent.go:235-242): cut a segment's runs after its terminating chunk
+//   sse_stream_kernel_v2 (SSE_FLAG_KERNEL_V2)  the earlier fused design: every warp an autonomous producer/consumer
+//       (stage + split + classify + serialize, ring of work items, the same automaton as consumer); kept for the tests
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "sse_common.cuh"
