@@ -7,6 +7,8 @@
  *   ssegw_pump                      one tick of the per-GPU batcher
  *   ssegw_recv                      `line, ok := <-streamCh` (api/routes.go:602-606, mcp/agent.go:171)
  *   ssegw_agent_recv and friends    mcp.Agent.RunWithStream for one iteration (mcp/agent.go:126-290, final [DONE] :140-143)
+ *   ssegw_mcp_writer_step           one turn of handleMCPStreamingRequest's writer (api/middlewares/mcp.go:253-299): the
+ *                                   terminal-frame rule (:261-268) and the upstream-error sniff that may set 503 (:272-280)
  */
 #ifndef SSE_GATEWAY_H
 #define SSE_GATEWAY_H
@@ -31,6 +33,14 @@ sse_bytes ssegw_agent_content(ssegw *g, int stream);
 int    ssegw_agent_has_tool_calls(ssegw *g, int stream);
 int    ssegw_agent_terminated(ssegw *g, int stream, int *finish);
 size_t ssegw_agent_tool_calls(ssegw *g, int stream, sse_tool_call *calls, size_t cap);
+
+/* The MCP writer (api/middlewares/mcp.go:253-299) for one element of the agent's channel. The frame is always written
+ * unchanged. Returns 1 when the stream ends after this write (the frame is byte-equal to "data: [DONE]\n\n", :261-268),
+ * else 0. *set_503 becomes 1 when the reference would call WriteHeader(503) for this frame (:272-280): it starts with
+ * "data: {", contains "\"error\"", and json.Unmarshal(frame[6:], &struct{ Error string `json:"error"` }) returns nil --
+ * i.e. the rest is valid JSON whose top-level keys matching "error" (exactly or case-insensitively) all hold a string or
+ * null. Pure host code (no device involved): such frames are rare and the status is not part of the byte stream. */
+int ssegw_mcp_writer_step(const uint8_t *frame, size_t n, int *set_503);
 
 #ifdef __cplusplus
 }

@@ -133,6 +133,9 @@ def load(build_if_missing: bool = True):
     L.sse_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.sse_at.argtypes = [C.POINTER(Result), u32]
     L.sse_at.restype = C.POINTER(C.c_uint8)
+    if hasattr(L, "ssegw_mcp_writer_step"):
+        L.ssegw_mcp_writer_step.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
+        L.ssegw_mcp_writer_step.restype = C.c_int
     L.sse_agent_new.restype = vp
     L.sse_agent_free.argtypes = [vp]
     L.sse_agent_free.restype = None

@@ -187,4 +187,156 @@ size_t ssegw_agent_tool_calls(ssegw *g, int id, sse_tool_call *calls, size_t cap
     return sse_agent_tool_calls(g->streams[(size_t)id].agent, calls, cap);
 }
 
+// ---- handleMCPStreamingRequest's writer, one channel element (api/middlewares/mcp.go:253-299)
+namespace {
+
+// encoding/json's checkValid + a walk of the top-level object, enough to tell whether
+// json.Unmarshal(data, &struct{ Error string `json:"error"` }) returns nil. Iterative (Go's nesting limit is 10000).
+struct ErrSniff {
+    const uint8_t *p, *e;
+    bool ws() { while (p < e && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) p++; return p < e; }
+    static int hexv(uint8_t c) { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; }
+    // scans a string starting at the opening quote; appends the unquoted bytes to *out when given
+    bool str(std::string *out) {
+        p++;
+        while (p < e) {
+            uint8_t c = *p;
+            if (c == '"') { p++; return true; }
+            if (c < 0x20) return false;
+            if (c != '\\') { if (out) out->push_back((char)c); p++; continue; }
+            if (++p >= e) return false;
+            c = *p++;
+            switch (c) {
+            case '"': case '\\': case '/': if (out) out->push_back((char)c); break;
+            case 'b': if (out) out->push_back('\b'); break;
+            case 'f': if (out) out->push_back('\f'); break;
+            case 'n': if (out) out->push_back('\n'); break;
+            case 'r': if (out) out->push_back('\r'); break;
+            case 't': if (out) out->push_back('\t'); break;
+            case 'u': {
+                if (e - p < 4) return false;
+                int v = 0;
+                for (int k = 0; k < 4; k++) { int h = hexv(p[k]); if (h < 0) return false; v = v * 16 + h; }
+                p += 4;
+                // only ASCII matters for the comparison with "error"; anything else makes the key differ
+                if (out) out->push_back(v < 0x80 ? (char)v : (char)0xFF);
+                break;
+            }
+            default: return false;
+            }
+        }
+        return false;
+    }
+    bool number() {
+        if (p < e && *p == '-') p++;
+        if (p >= e) return false;
+        if (*p == '0') p++;
+        else if (*p >= '1' && *p <= '9') { while (p < e && *p >= '0' && *p <= '9') p++; }
+        else return false;
+        if (p < e && *p == '.') { p++; if (p >= e || *p < '0' || *p > '9') return false; while (p < e && *p >= '0' && *p <= '9') p++; }
+        if (p < e && (*p == 'e' || *p == 'E')) {
+            p++;
+            if (p < e && (*p == '+' || *p == '-')) p++;
+            if (p >= e || *p < '0' || *p > '9') return false;
+            while (p < e && *p >= '0' && *p <= '9') p++;
+        }
+        return true;
+    }
+    bool lit(const char *w) { size_t n = strlen(w); if ((size_t)(e - p) < n || memcmp(p, w, n) != 0) return false; p += n; return true; }
+    static bool is_error_key(const std::string &k) {
+        if (k.size() != 5) return false;
+        static const char want[] = "error";
+        for (int i = 0; i < 5; i++) { char c = k[i]; if (c >= 'A' && c <= 'Z') c = (char)(c + 32); if (c != want[i]) return false; }
+        return true;
+    }
+    // returns true when Unmarshal would return nil
+    bool run() {
+        std::vector<uint8_t> stk;     // 1 = object, 0 = array
+        bool type_ok = true;
+        if (!ws() || *p != '{') return false;       // (the caller checked the "data: {" prefix; kept for completeness)
+        // state machine over values
+        enum { VALUE, AFTER } st = VALUE;
+        bool pending_error_key = false;             // the value about to be read belongs to a top-level "error" key
+        for (;;) {
+            if (st == VALUE) {
+                if (!ws()) return false;
+                const uint8_t c = *p;
+                const bool top = stk.size() == 1 && stk.back() == 1;
+                const bool chk = top && pending_error_key;
+                if (c == '{' || c == '[') {
+                    if (chk) type_ok = false;
+                    pending_error_key = false;
+                    if (stk.size() >= 10000) return false;
+                    stk.push_back(c == '{');
+                    p++;
+                    if (!ws()) return false;
+                    if (c == '{') {
+                        if (*p == '}') { p++; stk.pop_back(); st = AFTER; continue; }
+                        // key
+                        if (*p != '"') return false;
+                        std::string key; const bool want_key = stk.size() == 1;
+                        if (!str(want_key ? &key : nullptr)) return false;
+                        if (want_key) pending_error_key = is_error_key(key);
+                        if (!ws() || *p != ':') return false;
+                        p++;
+                        continue;
+                    }
+                    if (*p == ']') { p++; stk.pop_back(); st = AFTER; continue; }
+                    continue;
+                }
+                if (stk.empty()) return false;
+                if (c == '"') { if (!str(nullptr)) return false; }
+                else if (c == '-' || (c >= '0' && c <= '9')) { if (!number()) return false; if (chk) type_ok = false; }
+                else if (c == 't') { if (!lit("true")) return false; if (chk) type_ok = false; }
+                else if (c == 'f') { if (!lit("false")) return false; if (chk) type_ok = false; }
+                else if (c == 'n') { if (!lit("null")) return false; }
+                else return false;
+                pending_error_key = false;
+                st = AFTER;
+                continue;
+            }
+            // AFTER a value
+            if (stk.empty()) { ws(); return p == e && type_ok; }
+            if (!ws()) return false;
+            if (stk.back() == 1) {
+                if (*p == '}') { p++; stk.pop_back(); continue; }
+                if (*p != ',') return false;
+                p++;
+                if (!ws() || *p != '"') return false;
+                std::string key; const bool want_key = stk.size() == 1;
+                if (!str(want_key ? &key : nullptr)) return false;
+                if (want_key) pending_error_key = is_error_key(key);
+                if (!ws() || *p != ':') return false;
+                p++;
+                st = VALUE;
+            } else {
+                if (*p == ']') { p++; stk.pop_back(); continue; }
+                if (*p != ',') return false;
+                p++;
+                st = VALUE;
+            }
+        }
+    }
+};
+
+bool contains(const uint8_t *h, size_t n, const char *needle) {
+    const size_t m = strlen(needle);
+    if (n < m) return false;
+    for (size_t i = 0; i + m <= n; i++) if (h[i] == (uint8_t)needle[0] && memcmp(h + i, needle, m) == 0) return true;
+    return false;
+}
+
+} // namespace
+
+int ssegw_mcp_writer_step(const uint8_t *frame, size_t n, int *set_503) {
+    static const char done[] = "data: [DONE]\n\n";
+    if (set_503) *set_503 = 0;
+    if (n == sizeof(done) - 1 && memcmp(frame, done, n) == 0) return 1;                 // mcp.go:261-268
+    if (n >= 7 && memcmp(frame, "data: {", 7) == 0 && contains(frame, n, "\"error\"")) {   // mcp.go:272-280
+        ErrSniff s{ frame + 6, frame + n };
+        if (s.run() && set_503) *set_503 = 1;
+    }
+    return 0;
+}
+
 } // extern "C"
