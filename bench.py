@@ -27,9 +27,6 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# stdout carries exactly one JSON line: NCCL's version banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-
 import numpy as np  # noqa: E402
 
 N_SLOTS = 3      # batches in flight on the end-to-end path: H2D, kernel and D2H of consecutive batches overlap
@@ -187,7 +184,19 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries exactly one JSON line: NCCL printf()s its version banner to stdout when the communicator is created
+        # (NCCL_DEBUG=VERSION/INFO), so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     from inference_gateway_b200 import SseEngine, shard as sh
     bodies, mode, n_events = build_workload(args.streams, rank, args.workload, args.n_content)
