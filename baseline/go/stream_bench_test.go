@@ -20,6 +20,7 @@ package baseline
 import (
 	"bytes"
 	"context"
+	"crypto/sha256"
 	"encoding/binary"
 	"encoding/json"
 	"fmt"
@@ -176,6 +177,45 @@ func run(b *testing.B, mode string) {
 	b.StopTimer()
 	b.ReportMetric(float64(total)/b.Elapsed().Seconds(), "chunks/s")
 	b.ReportMetric(float64(workers), "cores")
+}
+
+// TestDumpParity writes, per stream, the SHA-256 of what the unmodified reference emits in mode P and in mode R
+// (frames concatenated). `python tools/check_go_dump.py $SSE_WORKLOAD $SSE_DUMP` compares it with this repository's oracle:
+// the byte-level pin that DESIGN.md section 6 says is missing ("parity unpinned").
+//
+//	SSE_WORKLOAD=/tmp/c4.bin SSE_DUMP=/tmp/c4_go.jsonl go test -run TestDumpParity ./tests/
+func TestDumpParity(t *testing.T) {
+	streams := loadWorkload(t)
+	path := os.Getenv("SSE_DUMP")
+	if path == "" {
+		t.Skip("SSE_DUMP not set")
+	}
+	f, err := os.Create(path)
+	if err != nil {
+		t.Fatal(err)
+	}
+	defer f.Close()
+	ctx := context.Background()
+	for i, body := range streams {
+		hp := sha256.New()
+		ch, err := newProvider(body).StreamChatCompletions(ctx, types.CreateChatCompletionRequest{})
+		if err != nil {
+			t.Fatal(err)
+		}
+		nP := 0
+		for line := range ch {
+			hp.Write(line)
+			nP++
+		}
+		hr := sha256.New()
+		sink := make(chan []byte, 1<<16)
+		nR := reframe(ctx, body, sink)
+		close(sink)
+		for fr := range sink {
+			hr.Write(fr)
+		}
+		fmt.Fprintf(f, "{\"stream\":%d,\"p_frames\":%d,\"p_sha256\":\"%x\",\"r_frames\":%d,\"r_sha256\":\"%x\"}\n", i, nP, hp.Sum(nil), nR, hr.Sum(nil))
+	}
 }
 
 func BenchmarkStreamPassthrough(b *testing.B) { run(b, "P") }
