@@ -91,3 +91,22 @@ class Gateway:
 
     def release(self, sid: int):
         self.L.ssegw_release_stream(self.g, sid)
+
+    def mcp_write_loop(self, sid: int):
+        """handleMCPStreamingRequest's writer (api/middlewares/mcp.go:253-299) over the agent channel of one stream:
+        returns (bytes written to the client so far, status_503, ended). Call after pump() until ended."""
+        out = bytearray()
+        status_503 = False
+        while True:
+            try:
+                fr = self.agent_recv(sid)
+            except EOFError:                     # channel closed without the terminal frame (mcp.go:256-259)
+                return bytes(out), status_503, True
+            if fr is None:
+                return bytes(out), status_503, False
+            flag = C.c_int(0)
+            stop = self.L.ssegw_mcp_writer_step(fr, len(fr), C.byref(flag))
+            status_503 = status_503 or bool(flag.value)
+            out += fr
+            if stop:
+                return bytes(out), status_503, True

@@ -100,3 +100,25 @@ def test_provider_channel_passthrough_and_backpressure(gw):
     with pytest.raises(EOFError):
         gw.recv(sid)
     gw.release(sid)
+
+
+def test_mcp_writer_loop_terminal_frame_and_error_status(gw):
+    """api/middlewares/mcp.go:253-299 over the agent's channel (tests/middlewares/mcp_test.go:768-918 pins one [DONE] at the
+    end): every frame is written unchanged, the stream ends at the frame that is byte-equal to "data: [DONE]\\n\\n", and an
+    upstream error object seen on the way sets 503 without touching the bytes."""
+    sid = gw.stream_chat_completions(R)
+    body = (b'data: {"choices":[{"index":0,"delta":{"content":"partial"},"finish_reason":null}]}\n\n'
+            b'data: {"error": "upstream exploded"}\n\n'
+            b'data: {"choices":[{"index":0,"delta":{},"finish_reason":"stop"}]}\n\n'
+            b'data: {"choices":[],"usage":{"prompt_tokens":1,"completion_tokens":1,"total_tokens":2}}\n\ndata: [DONE]\n\n')
+    assert gw.upstream_write(sid, body) == len(body)
+    gw.pump()
+    gw.upstream_close(sid)
+    gw.pump()
+    written, status_503, ended = gw.mcp_write_loop(sid)
+    gw.release(sid)
+    assert ended and status_503
+    assert written == (b'data: {"choices":[{"index":0,"delta":{"content":"partial"},"finish_reason":null}]}\n\n'
+                       b'data: {"error": "upstream exploded"}\n\n'
+                       b'data: {"choices":[{"index":0,"delta":{},"finish_reason":"stop"}]}\n\n'
+                       b'data: [DONE]\n\n')       # the usage-only chunk after the terminating one is never read (agent.go:235-242)
