@@ -50,6 +50,18 @@ def test_strerror_and_argument_checks():
     ctx = C.c_void_p()
     bad = A.Config()
     assert L.sse_init(0, C.byref(bad), C.byref(ctx)) == A.SSE_ERR_ARG        # struct_size mismatch
+    # arena offsets are 31-bit (out arena + input arena share one address space, include/sse_gpu.h sse_at): a batch that
+    # cannot be addressed is refused up front, before any device is touched
+    big = A.Config()
+    L.sse_default_config(C.byref(big), 1024, 1 << 20)
+    big.in_arena_bytes = 1 << 30
+    big.out_arena_bytes = (1 << 30) + (1 << 29)
+    assert L.sse_init(0, C.byref(big), C.byref(ctx)) == A.SSE_ERR_ARG
+    # sse_at resolves both halves of the offset space
+    res = A.Result()
+    ob = (C.c_uint8 * 8)(*b"OUTARENA"); ib = (C.c_uint8 * 8)(*b"INPUTBUF")
+    res.out = C.cast(ob, C.POINTER(C.c_uint8)); res.in_ = C.cast(ib, C.POINTER(C.c_uint8)); res.in_base = 4096
+    assert L.sse_at(C.byref(res), 3)[0] == ord("A") and L.sse_at(C.byref(res), 4096 + 5)[0] == ord("B")
 
 
 def test_no_device_is_an_error_not_a_fallback():
