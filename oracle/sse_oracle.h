@@ -13,8 +13,13 @@
  *   - the reference's own SSE fixtures and the semantic assertions its tests make on them
  *     (tests/golden/ref_fixtures.json, produced by tools/make_golden.py),
  *   - SURVEY.md Appendix B hand-derived vectors,
- *   - a cross-check of the JSON validator/decoder against CPython's json module
- *     (tests/test_oracle_json.py).
+ *   - a cross-check of the JSON validator/decoder against CPython's json module and an
+ *     independent Python model of the typed decode (tests/go_model.py, tests/test_oracle_json.py),
+ *   - an independent Python model of everything above the decoder -- TrimSpace, the agent
+ *     iteration, parseStreamingToolCalls, telemetry (tests/go_stream_model.py,
+ *     tests/test_oracle_stream_model.py).
+ * None of these is a run of the Go code: tools/check_go_dump.py + baseline/go/ is the byte-level
+ * check for a machine that has Go.
  *
  * Functions and the reference code they restate:
  *   orc_split_lines       providers/core/provider.go:308-341 (ReadBytes('\n'), tail dropped)
