@@ -69,6 +69,7 @@ typedef struct {
 
 #define SSE_FLAG_KERNEL_V1 1u  /* fused first-generation kernel (sequential per-lane decoder) */
 #define SSE_FLAG_KERNEL_V2 2u  /* fused producer/consumer kernel (table-driven automaton); default is the split pipeline */
+#define SSE_FLAG_KERNEL_SPLIT 4u /* round-1 split pipeline (produce / sort / decode / finalize kernels) */
 #define SSE_FLAG_COPY_OUT 8u   /* materialise every frame in the out arena. Default: a frame whose bytes already stand in the
                                   caller's input arena exactly as the reference would send them (every mode P line, and a mode R
                                   "data: ...\n" line followed by a blank line) is returned as a span of the input arena and is
@@ -203,6 +204,10 @@ const char *sse_strerror(int status);
 const char *sse_last_cuda_error(void);
 int  sse_abi_version(void);
 void sse_default_config(sse_config *cfg, uint32_t max_conns, uint32_t bytes_per_batch);
+/* Capacities under which NO input can overflow a result arena (a batch of bytes_per_batch bytes on max_conns connections):
+ * memory grows to ~30x the batch size, meant for small batcher arenas (sse_gateway.h uses it). With sse_default_config the
+ * capacities fit realistic SSE traffic and a pathological batch fails as a whole with SSE_ERR_OVERFLOW. */
+void sse_worst_case_config(sse_config *cfg, uint32_t max_conns, uint32_t bytes_per_batch);
 
 /* pipeline: acquire -> fill -> submit -> collect -> release (one slot = one batch in flight) */
 int sse_acquire(sse_ctx *ctx, int *slot, sse_batch *batch);

@@ -86,7 +86,7 @@ class ToolCall(C.Structure):
 assert C.sizeof(Seg) == 16 and C.sizeof(Rec) == 32 and C.sizeof(Tc) == 48 and C.sizeof(SegResult) == 32
 
 EXPORTS = [
-    "sse_init", "sse_destroy", "sse_strerror", "sse_last_cuda_error", "sse_abi_version", "sse_default_config",
+    "sse_init", "sse_destroy", "sse_strerror", "sse_last_cuda_error", "sse_abi_version", "sse_default_config", "sse_worst_case_config",
     "sse_acquire", "sse_submit", "sse_collect", "sse_release", "sse_reset_conn", "sse_reset_all",
     "sse_upload", "sse_launch", "sse_download", "sse_launch_count", "sse_at",
     "sse_agent_new", "sse_agent_free", "sse_agent_reset", "sse_agent_feed", "sse_agent_content",

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libssegpu.so")
-SOURCES = ["sse_kernel.cu", "sse_kernel2.cu", "sse_host.cu", "sse_fold.cpp", "sse_gateway.cpp"]
+SOURCES = ["sse_fused.cu", "sse_kernel.cu", "sse_kernel2.cu", "sse_host.cu", "sse_fold.cpp", "sse_gateway.cpp"]
 HEADERS = ["sse_device.cuh", "sse_common.cuh", "sse_tables.h", os.path.join("..", "..", "include", "sse_gpu.h"),
            os.path.join("..", "..", "include", "sse_gateway.h")]
 

@@ -37,7 +37,8 @@ struct Counters {
     int32_t  status;
     uint32_t n_items;      // split pipeline: work items written by the produce kernel
     uint32_t item_ticket;  // split pipeline: next item batch for the decode kernel
-    uint32_t reserved0, reserved1;
+    uint32_t n_tiles;      // fused pipeline: tiles written by the plan kernel
+    uint32_t reserved1;
     uint32_t overflow;     // SSE_OVF_* bits: which arena was too small
     uint32_t pad[2];
     // device-only tail (the host reads the struct up to here)
@@ -69,6 +70,8 @@ struct KParams {
     uint32_t *seg_term;                            // per segment: smallest terminating record index, SSE_NONE if none
     uint32_t flags;                                // sse_config.flags
     uint4 *items_sorted;                           // items ordered by (length bucket, shape class): the 32 lanes of a decode batch walk alike lines
+    // fused pipeline (plan -> fused tile kernel)
+    uint2 *tiles;            uint32_t cap_tiles;   // {first segment, segment count} per tile
 };
 
 #ifdef __CUDACC__
@@ -84,3 +87,6 @@ int sse_launch_produce_kernel(const KParams &p, void *stream, int sm_count);    
 int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int device);  // split pipeline, stages 2+3
 int sse_v2_prepare(int device);                                                        // builds + uploads the automaton tables
 int sse_launch_stream_kernel_v2(const KParams &p, void *stream, int sm_count, int device);
+int sse_fused_prepare(int device);                                                     // fused pipeline: tables + kernel attributes
+int sse_launch_fused(const KParams &p, void *stream, int sm_count, int device);        // plan kernel + fused tile kernel
+uint32_t sse_fused_max_line(void);                                                     // longest carry_slot_bytes the fused kernel supports

@@ -26,6 +26,7 @@
 namespace {
 
 constexpr size_t CHAN_CAP = 100;
+constexpr size_t PENDING_CAP = 4u << 20;   // per-stream bytes waiting for a batch
 
 struct Stream {
     bool open = false;          // slot in use
@@ -46,14 +47,16 @@ struct ssegw {
     sse_config cfg{};
     std::vector<Stream> streams;
     std::string last_error;
+    size_t rr = 0;              // the batcher starts its scan one stream further every tick (no slot is favoured)
 };
 
 extern "C" {
 
 ssegw *ssegw_new(int device, uint32_t max_conns, uint32_t bytes_per_batch, int *status) {
     ssegw *g = new ssegw();
-    sse_default_config(&g->cfg, max_conns, bytes_per_batch);
-    g->cfg.carry_slot_bytes = 65536;
+    // worst-case result capacities: whatever the upstreams send (a flood of one-byte lines, of empty tool-call elements ...), a
+    // batch cannot overflow, so one connection can never fail the batch of the others
+    sse_worst_case_config(&g->cfg, max_conns, bytes_per_batch);
     int rc = sse_init(device, &g->cfg, &g->ctx);
     if (status) *status = rc;
     if (rc != SSE_OK) { delete g; return nullptr; }   // no CUDA device: error, never a CPU path
@@ -87,6 +90,9 @@ size_t ssegw_upstream_write(ssegw *g, int id, const uint8_t *data, size_t n) {
     Stream &s = g->streams[(size_t)id];
     if (!s.open || s.upstream_eof || s.closed) return 0;
     if (s.chan.size() >= CHAN_CAP) return 0;
+    // bytes not yet handed to the GPU are bounded like a socket buffer: a reader that outruns the batcher is told to wait
+    const size_t room = s.pending.size() < PENDING_CAP ? PENDING_CAP - s.pending.size() : 0;
+    if (n > room) n = room;
     s.pending.append((const char *)data, n);
     return n;
 }
@@ -100,16 +106,21 @@ int ssegw_pump(ssegw *g) {
     if (rc != SSE_OK) return rc;
     std::vector<uint32_t> who;
     uint32_t off = 0, n = 0;
-    for (size_t i = 0; i < g->streams.size(); i++) {
+    const size_t ns = g->streams.size();
+    const size_t start = ns ? g->rr++ % ns : 0;
+    for (size_t q = 0; q < ns && n < b.max_segs; q++) {
+        const size_t i = (start + q) % ns;
         Stream &s = g->streams[i];
         if (!s.open || s.closed || s.pending.empty()) continue;
         if (s.chan.size() >= CHAN_CAP) continue;                      // receiver is slow: leave the bytes queued
-        size_t take = s.pending.size();
-        if (n >= b.max_segs || off + take + 16 > b.in_arena_bytes) break;
+        // a stream takes what fits: the rest stays queued for the next tick (the carry state on the device makes any cut legal)
+        const size_t room = b.in_arena_bytes > off + 16u ? (size_t)(b.in_arena_bytes - off - 16u) : 0;
+        const size_t take = s.pending.size() < room ? s.pending.size() : room;
+        if (take == 0) continue;
         memcpy(b.in_arena + off, s.pending.data(), take);
         b.segs[n] = sse_seg{ (uint32_t)i, off, (uint32_t)take, s.mode, 0, 0 };
         off = (off + (uint32_t)take + 15u) & ~15u;
-        s.pending.clear();
+        s.pending.erase(0, take);
         who.push_back((uint32_t)i);
         n++;
     }

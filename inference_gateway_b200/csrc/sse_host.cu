@@ -44,6 +44,7 @@ struct Slot {
     Counters *d_ctr = nullptr;
     uint4 *d_items = nullptr; uint32_t *d_segterm = nullptr;   // split pipeline scratch (device only)
     uint4 *d_items2 = nullptr;                                 // items ordered for the decode kernel
+    uint2 *d_tiles = nullptr;                                  // fused pipeline: tile list of the plan kernel
     uint32_t n_segs = 0, in_bytes = 0;
 };
 
@@ -79,7 +80,7 @@ void free_slot(Slot &s) {
     cudaFreeHost(s.h_ctr);
     cudaFree(s.d_segs); cudaFree(s.d_out);   // d_in lives inside d_out's allocation
     cudaFree(s.d_frames); cudaFree(s.d_recs); cudaFree(s.d_tcs);
-    cudaFree(s.d_usages); cudaFree(s.d_text); cudaFree(s.d_runs); cudaFree(s.d_segres); cudaFree(s.d_ctr); cudaFree(s.d_items); cudaFree(s.d_segterm); cudaFree(s.d_items2);
+    cudaFree(s.d_usages); cudaFree(s.d_text); cudaFree(s.d_runs); cudaFree(s.d_segres); cudaFree(s.d_ctr); cudaFree(s.d_items); cudaFree(s.d_segterm); cudaFree(s.d_items2); cudaFree(s.d_tiles);
 }
 
 KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
@@ -96,6 +97,7 @@ KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
     p.seg_results = s.d_segres; p.ctr = s.d_ctr;
     p.items = s.d_items; p.cap_items = c->cfg.max_recs; p.seg_term = s.d_segterm;
     p.items_sorted = s.d_items2; p.flags = c->cfg.flags;
+    p.tiles = s.d_tiles; p.cap_tiles = c->cfg.max_segs + 64;
     return p;
 }
 
@@ -123,7 +125,11 @@ int do_launch(sse_ctx *c, Slot &s, uint32_t n_segs, cudaStream_t st) {
         int e;
         if (c->cfg.flags & SSE_FLAG_KERNEL_V1) { e = sse_launch_stream_kernel(p, (void *)st, c->sm_count); c->launches += 1; }
         else if (c->cfg.flags & SSE_FLAG_KERNEL_V2) { e = sse_launch_stream_kernel_v2(p, (void *)st, c->sm_count, c->device); c->launches += 1; }
-        else {   // default: split pipeline produce -> decode -> finalize
+        else if (!(c->cfg.flags & SSE_FLAG_KERNEL_SPLIT)) {   // default: plan + fused tile kernel
+            e = sse_launch_fused(p, (void *)st, c->sm_count, c->device);
+            c->launches += 2;
+        }
+        else {   // round-1 split pipeline produce -> decode -> finalize
             e = sse_launch_produce_kernel(p, (void *)st, c->sm_count);
             if (e == 0) e = sse_launch_decode_finalize(p, (void *)st, c->sm_count, c->device);
             c->launches += 6;   // produce, bucket hist/scan/scatter, decode, finalize
@@ -205,10 +211,24 @@ void sse_default_config(sse_config *cfg, uint32_t max_conns, uint32_t bytes_per_
     cfg->n_slots = 2;
 }
 
+void sse_worst_case_config(sse_config *cfg, uint32_t max_conns, uint32_t bytes_per_batch) {
+    sse_default_config(cfg, max_conns, bytes_per_batch);
+    const uint64_t in = cfg->in_arena_bytes, cap = 0xF0000000ull;
+    auto clamp = [&](uint64_t v) { return (uint32_t)(v > cap ? cap : v); };
+    cfg->carry_slot_bytes = 65504;                                   // longest line the fused kernel supports
+    cfg->max_frames = clamp(in + 64);                                // a frame needs its own '\n' in this batch
+    cfg->max_recs = clamp(in / 4 + 2ull * max_conns + 64);           // "data: x\n" is 8 bytes; one carried line per segment
+    cfg->max_usages = cfg->max_recs;
+    cfg->max_tcs = clamp(in / 3 + 64);                               // "{}," per element
+    cfg->text_arena_bytes = clamp(4 * in + 65536);                   // U+FFFD for every invalid byte: 1 -> 3, 4-byte aligned
+    cfg->out_arena_bytes = clamp(in + in / 4 + (uint64_t)max_conns * (cfg->carry_slot_bytes + 32ull) + (1u << 20));
+    cfg->max_runs = clamp(in / 256 + 2ull * max_conns + 1024);
+}
+
 int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
     if (!cfg || !out || cfg->struct_size != sizeof(sse_config)) return SSE_ERR_ARG;
     if (cfg->n_slots < 1 || cfg->n_slots > 8 || cfg->max_conns == 0 || cfg->max_segs == 0 ||
-        (cfg->in_arena_bytes & 15u) || cfg->carry_slot_bytes < 8192 + 16) return SSE_ERR_ARG;
+        (cfg->in_arena_bytes & 15u) || cfg->carry_slot_bytes < 8192 + 16 || (cfg->carry_slot_bytes & 15u)) return SSE_ERR_ARG;
     if ((uint64_t)in_base_of(*cfg) + cfg->in_arena_bytes + 16 >= (1ull << 31)) return SSE_ERR_ARG;   // arena offsets are 31-bit
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) {
@@ -222,9 +242,13 @@ int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
     cudaDeviceProp prop;
     if (!cu_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete c; return SSE_ERR_CUDA; }
     c->sm_count = prop.multiProcessorCount;
-    if (!(cfg->flags & SSE_FLAG_KERNEL_V1)) {
+    if (cfg->flags & (SSE_FLAG_KERNEL_V2 | SSE_FLAG_KERNEL_SPLIT)) {
         int e2 = sse_v2_prepare(device);
         if (e2 != 0) { cu_ok((cudaError_t)e2, "sse_v2_prepare"); delete c; return SSE_ERR_CUDA; }
+    } else if (!(cfg->flags & SSE_FLAG_KERNEL_V1)) {
+        if (cfg->carry_slot_bytes > sse_fused_max_line()) { delete c; return SSE_ERR_ARG; }
+        int e2 = sse_fused_prepare(device);
+        if (e2 != 0) { cu_ok((cudaError_t)e2, "sse_fused_prepare"); delete c; return SSE_ERR_CUDA; }
     }
     bool ok = true;
     ok = ok && cu_ok(cudaStreamCreateWithFlags(&c->ctl_stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -249,6 +273,7 @@ int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
         ok = ok && dalloc(s.d_runs, cfg->max_runs) && dalloc(s.d_segres, cfg->max_segs) && dalloc(s.d_ctr, 1);
         ok = ok && dalloc(s.d_items, cfg->max_recs) && dalloc(s.d_segterm, cfg->max_segs);
         ok = ok && dalloc(s.d_items2, cfg->max_recs);
+        ok = ok && dalloc(s.d_tiles, (size_t)cfg->max_segs + 64);
     }
     if (!ok) { sse_destroy(c); return SSE_ERR_CUDA; }
     *out = c;
