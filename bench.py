@@ -5,14 +5,17 @@ A step = one pass of the hot path over one micro-batch of synthetic SSE input: w
 (65,536 concurrent mixed cohere/groq/anthropic/ollama streams incl. tool_calls deltas, ~512 B mean chunk,
 mode R = MCP reframe + JSON side-band) per GPU, every stream complete in the batch (11 SSE events).
 
-  value   emitted chunks/s with the batch already resident in HBM (kernel path only, CUDA events)
-  e2e     the same through the C ABI a caller uses (sse_submit/sse_collect): pinned H2D + kernel + D2H per step
-  roofline  algorithmic bytes of the stream kernel / its measured duration vs the measured HBM peak
-  cpu_baseline  the CPU oracle port (oracle/, test infrastructure) timed on a bounded sample on the host cores
+  value      emitted chunks/s with the batch already resident in HBM (plan + fused kernel, CUDA events); the timed steps
+             rotate over three resident copies of the input, so no step finds its input in L2
+  segmented  the same streams cut into k seeded TCP pieces: a step is k launches, the unterminated tails travel through
+             the per-connection carry slots (no reset between the pieces)
+  c5_strong  (N > 1) ONE population of --streams connections sharded by hash(conn_id) % N (BASELINE configs[4])
+  e2e        through the C ABI a caller uses (sse_submit/sse_collect): pinned H2D + kernels + D2H per step
+  roofline   algorithmic bytes of the step / its measured duration vs the measured HBM peak
+  cpu_baseline  the CPU oracle port (oracle/, test infrastructure) on the host cores, same streams
 
-Multi-GPU (torchrun, one rank per GPU): connections shard by hash(conn_id) % N, no collective on the data path
-(weak scaling: 65,536 streams per GPU). `--impl reference` times the reference's CPU path (the oracle port: the
-reference is Go and cannot be built here) on the host cores.
+Multi-GPU (torchrun, one rank per GPU): connections shard by hash(conn_id) % N, no collective on the data path.
+`--impl reference` times the reference's CPU path (the oracle port: the reference is Go and cannot be built here).
 """
 from __future__ import annotations
 
@@ -29,9 +32,16 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-N_SLOTS = 3      # batches in flight on the end-to-end path: H2D, kernel and D2H of consecutive batches overlap
+N_SLOTS = 4      # device-resident copies / batches in flight
+N_ROT = 3        # resident input copies the timed steps rotate over
 METRIC = "SSE chunks/sec @ 64k concurrent streams"
 UNIT = "chunks/s"
+WORKLOADS = {
+    "C2": "C2: {n} concurrent OpenAI streams, passthrough (identity remap), 256 B mean chunk, mode P",
+    "C3": "C3: {n} concurrent Anthropic (OpenAI-compatible) streams, 512 B mean chunk, mode R (MCP reframe + JSON side-band)",
+    "C4": "C4: {n} concurrent mixed cohere/groq/anthropic/ollama streams incl. tool_calls deltas, 512 B mean chunk, "
+          "mode R (MCP reframe + JSON side-band)",
+}
 
 
 def log(*a):
@@ -43,6 +53,14 @@ def env_int(name, default):
         return int(os.environ.get(name, default))
     except ValueError:
         return default
+
+
+def host_threads() -> int:
+    """Cores this process may run on (the cgroup / affinity of a 1-GPU lease is smaller than os.cpu_count())."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
 
 
 def build_workload(n_streams: int, shard: int, workload: str, n_content=None):
@@ -112,48 +130,72 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(bodies, mode, threads: int, target_s: float = 3.0):
-    """Times the oracle port (CPU restatement of the reference path) on a bounded sample of the workload."""
-    from oracle import orc
-    sample = bodies[:min(len(bodies), 16384)]
-    arena = np.frombuffer(b"".join(sample), dtype=np.uint8)
-    lens = np.fromiter((len(b) for b in sample), dtype=np.uint32, count=len(sample))
-    offs = np.zeros(len(sample), dtype=np.uint64)
+def _oracle_arrays(bodies, mode):
+    arena = np.frombuffer(b"".join(bodies), dtype=np.uint8)
+    lens = np.fromiter((len(b) for b in bodies), dtype=np.uint32, count=len(bodies))
+    offs = np.zeros(len(bodies), dtype=np.uint64)
     offs[1:] = np.cumsum(lens.astype(np.uint64))[:-1]
-    modes = np.full(len(sample), mode, dtype=np.uint8)
-    orc.bench_run(arena, offs, lens, modes, threads)           # warm-up (page in, allocator)
-    total_s, frames, passes = 0.0, 0, 0
-    while total_s < target_s and passes < 64:
-        secs, _, fr, _ = orc.bench_run(arena, offs, lens, modes, threads)
-        total_s += secs; frames += fr; passes += 1
-    return {"value": frames / total_s, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{len(sample)} streams of the workload x {passes} passes, {arena.size / 1e6:.0f} MB per pass, "
-                      f"{total_s:.1f} s of CPU wall time; oracle/sse_oracle.c (C restatement; the reference is Go and no Go "
-                      f"toolchain exists on this box)"}
+    return arena, offs, lens, np.full(len(bodies), mode, dtype=np.uint8)
+
+
+def cpu_baseline(bodies, mode, threads: int, target_s: float = 3.0, with_single: bool = True):
+    """Times the oracle port (CPU restatement of the reference path) on the SAME streams as the GPU arm: one pool of
+    `threads` threads, enough passes over all streams for >= target_s seconds of wall time."""
+    from oracle import orc
+    arena, offs, lens, modes = _oracle_arrays(bodies, mode)
+    secs, _, fr1, _ = orc.bench_run(arena, offs, lens, modes, threads, 1)          # warm-up pass (page in, allocators); sizes the run
+    passes = int(max(1, min(64, np.ceil(target_s / max(secs, 1e-3)))))
+    secs, _, frames, _ = orc.bench_run(arena, offs, lens, modes, threads, passes)
+    out = {"value": frames / secs, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": f"all {len(bodies)} streams of the workload x {passes} passes ({arena.size / 1e6:.0f} MB per pass), "
+                     f"{secs:.1f} s of wall time, one pool of {threads} threads; oracle/sse_oracle.c (C restatement; the "
+                     f"reference is Go and no Go toolchain exists on this box)"}
+    if with_single:
+        sub = max(1, len(bodies) // 8)
+        a1, o1, l1, m1 = _oracle_arrays(bodies[:sub], mode)
+        s1, _, f1, _ = orc.bench_run(a1, o1, l1, m1, 1, 1)
+        out["value_1_thread"] = f1 / s1
+        out["sample"] += f"; 1 thread: the first {sub} streams once, {s1:.1f} s"
+    return out
+
+
+def workload_text(args):
+    return WORKLOADS.get(args.workload, args.workload + ": {n} streams").format(n=args.streams)
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port) with all host threads, rank 0 only."""
+    """--impl reference: the reference's CPU path (oracle port) with all host threads, rank 0 only, on the GPU arm's streams."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    bodies, mode, _ = build_workload(min(args.streams, 16384), 0, args.workload)
+    threads = host_threads()
+    bodies, mode, _ = build_workload(args.streams, 0, args.workload)
+    if args.mode is not None:
+        mode = args.mode
     vals = []
     for _ in range(args.warmup):
-        cpu_baseline(bodies, mode, threads, target_s=0.5)
+        cpu_baseline(bodies, mode, threads, target_s=0.3, with_single=False)
     for _ in range(args.steps):
-        vals.append(cpu_baseline(bodies, mode, threads, target_s=2.0))
+        vals.append(cpu_baseline(bodies, mode, threads, target_s=1.5, with_single=False))
     v = statistics.mean(x["value"] for x in vals)
     cb = dict(vals[-1]); cb["value"] = v
-    chunks_per_step = None
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: mixed cohere/groq/anthropic/ollama SSE streams, mode R (reframe + side-band), "
-                                   f"bounded sample of {len(bodies)} streams per step", "threads": threads},
+            "config": {"workload": workload_text(args), "streams_per_gpu": args.streams, "threads": threads,
+                       "parity": "parity unpinned: the arm is the C restatement of the Go path (oracle/), not a Go run"},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def time_steps(torch, fn, steps):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        fn(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1)
 
 
 def main():
@@ -162,15 +204,20 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=65536, help="concurrent streams per GPU")
-    ap.add_argument("--workload", default="C4")
+    ap.add_argument("--streams", type=int, default=None, help="concurrent streams per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", type=int, default=None, help="override the workload's mode bits (0 P, 2 P+parse, 3 R+parse)")
-    ap.add_argument("--flags", type=int, default=0, help="sse_config.flags (1 v1 kernel, 2 fused v2 kernel, 8 copy-out)")
+    ap.add_argument("--flags", type=int, default=0, help="sse_config.flags (1 v1 kernel, 4 round-1 split pipeline, 8 copy-out, 16 no templates)")
+    ap.add_argument("--segments", type=int, default=4, help="TCP pieces per stream of the segmented measurement (0: skip it)")
     ap.add_argument("--n-content", type=int, default=None, help="content deltas per stream (default: the config's 7)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.streams is None:
+        args.streams = {"C2": 4096, "C3": 16384, "C4": 65536}[args.workload]
+    args.segments = max(0, min(args.segments, N_SLOTS))
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
@@ -198,7 +245,8 @@ def main():
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
-    from inference_gateway_b200 import SseEngine, shard as sh
+    from inference_gateway_b200 import SseEngine, shard as sh, synth
+    # weak scaling: every rank owns its own population of --streams connections (seeded by the rank)
     bodies, mode, n_events = build_workload(args.streams, rank, args.workload, args.n_content)
     if args.mode is not None:
         mode = args.mode
@@ -211,19 +259,30 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
 
-    slot, arena, segs = eng.acquire()
-    n_segs, in_bytes, _ = fill_slot(eng, arena, segs, bodies, mode)
-    eng.upload(slot, n_segs, in_bytes, stream)
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident input: N_ROT copies, the timed steps rotate over them (no step finds its input in L2)
+    slots = []
+    for _ in range(N_SLOTS):
+        sl, arena, segs = eng.acquire()
+        slots.append((sl, arena, segs))
+    n_segs = in_bytes = 0
+    for sl, arena, segs in slots[:N_ROT]:
+        n_segs, in_bytes, _ = fill_slot(eng, arena, segs, bodies, mode)
+        eng.upload(sl, n_segs, in_bytes, stream)
     torch.cuda.synchronize()
 
-    def step():
+    def step(i):
         eng.reset_all(stream)          # a step = a fresh population of connections
-        eng.launch(slot, n_segs, stream)
+        eng.launch(slots[i % N_ROT][0], n_segs, stream)
 
-    for _ in range(args.warmup):
-        step()
+    for i in range(args.warmup):
+        step(i)
     torch.cuda.synchronize()
-    res = eng.download(slot, stream)   # untimed: counts for the report + sanity
+    res = eng.download(slots[(args.warmup - 1) % N_ROT][0], stream)   # untimed: counts for the report + sanity
     counts = dict(frames=int(res.raw.n_frames), recs=int(res.raw.n_recs), tcs=int(res.raw.n_tcs), usages=int(res.raw.n_usages),
                   out_bytes=int(res.raw.out_bytes), text_bytes=int(res.raw.text_bytes), runs=int(res.raw.n_runs),
                   in_bytes=in_payload, segs=n_segs, events=n_events)
@@ -242,46 +301,96 @@ def main():
     terminated = int(np.count_nonzero(res.segs["flags"] & 1))
     ok_recs = int(np.count_nonzero(res.recs["flags"] & 1))
 
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    sync_all()
     sampler = ClockSampler(local_rank)
     # nvidia-smi needs a few hundred ms before its first sample: keep the GPU under the same load (untimed) meanwhile,
     # so that the clock samples bracket the timed region and are all taken under load
     t_pre = time.perf_counter()
+    i = 0
     while time.perf_counter() - t_pre < 1.2:
-        step()
+        step(i); i += 1
         torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    sync_all()
     launches0 = eng.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms = time_steps(torch, step, args.steps)
+    sync_all()
     launches = eng.launch_count() - launches0
     clocks = sampler.stop()
 
-    # ---- end to end through the public C ABI: pinned H2D + kernel + D2H every step, two slots in flight
+    # ---- the same streams in k seeded TCP pieces: a step is k launches, tails go through the carry slots
+    segmented = None
+    if args.segments >= 2:
+        k = args.segments
+        rng = np.random.default_rng(0xB200)
+        pieces = [synth.random_cuts(rng, b, k) for b in bodies]
+        piece_meta = []
+        for b_i, (sl, arena, segs) in enumerate(slots[:k]):
+            part = [p[b_i] if b_i < len(p) else b"" for p in pieces]
+            ns, nb, _ = fill_slot(eng, arena, segs, part, mode)
+            eng.upload(sl, ns, nb, stream)
+            piece_meta.append((sl, ns))
+        torch.cuda.synchronize()
+
+        def seg_step(_i):
+            eng.reset_all(stream)
+            for sl, ns in piece_meta:
+                eng.launch(sl, ns, stream)
+
+        for i in range(3):
+            seg_step(i)
+        torch.cuda.synchronize()
+        seg_frames = 0
+        for sl, ns in piece_meta:      # frames of the last warm-up step (sanity: the same chunks come out)
+            r = eng.download(sl, stream)
+            seg_frames += int(r.segs["frame_count"].astype(np.int64).sum()) + sum(int(r.runs["frame_count"][j]) for j in range(int(r.raw.n_runs)))
+        sync_all()
+        seg_ms = sh.max_over_ranks(time_steps(torch, seg_step, args.steps), world)
+        seg_tot = sh.reduce_counters({"f": seg_frames}, world)["f"]
+        segmented = {"pieces_per_stream": k, "launches_per_step": 2 * k, "value": seg_tot * args.steps / (seg_ms / 1e3), "unit": UNIT,
+                     "ms_per_step": seg_ms / args.steps, "chunks_emitted_per_step": seg_tot,
+                     "note": "seeded random TCP cuts; every piece is its own micro-batch, unterminated tails are carried on the device"}
+        if seg_frames != counts["frames"]:
+            segmented["warning"] = f"emitted {seg_frames} chunks, the one-shot batch emitted {counts['frames']}"
+
+    # ---- BASELINE configs[4]: ONE population of --streams connections sharded over the ranks by hash(conn_id) % N
+    strong = None
+    if world > 1 and not args.no_strong:
+        g_bodies, _, _ = build_workload(args.streams, 0, args.workload, args.n_content)
+        mine = np.nonzero(sh.shard_of(np.arange(len(g_bodies), dtype=np.uint64), world) == rank)[0]
+        my = [g_bodies[int(c)] for c in mine]
+        s_meta = []
+        for sl, arena, segs in slots[:N_ROT]:
+            ns, nb, _ = fill_slot(eng, arena, segs, my, mode)
+            eng.upload(sl, ns, nb, stream)
+            s_meta.append((sl, ns))
+        torch.cuda.synchronize()
+
+        def strong_step(i):
+            eng.reset_all(stream)
+            eng.launch(s_meta[i % N_ROT][0], s_meta[i % N_ROT][1], stream)
+
+        for i in range(3):
+            strong_step(i)
+        torch.cuda.synchronize()
+        r = eng.download(s_meta[2][0], stream)
+        s_frames = int(r.segs["frame_count"].astype(np.int64).sum()) + sum(int(r.runs["frame_count"][j]) for j in range(int(r.raw.n_runs)))
+        sync_all()
+        s_ms = sh.max_over_ranks(time_steps(torch, strong_step, args.steps), world)
+        s_tot = sh.reduce_counters({"f": s_frames, "n": len(my)}, world)
+        strong = {"scaling": "strong", "total_streams": s_tot["n"], "value": s_tot["f"] * args.steps / (s_ms / 1e3), "unit": UNIT,
+                  "ms_per_step": s_ms / args.steps, "sharding": "shard_of(conn_id) = fibonacci hash % n_gpus (inference_gateway_b200/shard.py)"}
+
+    # ---- end to end through the public C ABI: pinned H2D + kernels + D2H every step, three slots in flight
     e2e = None
     if not args.no_e2e:
-        eng.release(slot)
-        slots = []
-        for _ in range(N_SLOTS):
-            s2, a2, g2 = eng.acquire()
-            fill_slot(eng, a2, g2, bodies, mode)
-            slots.append(s2)
-        for s2 in slots:
-            eng.release(s2)
+        for sl, arena, segs in slots:
+            fill_slot(eng, arena, segs, bodies, mode)
+        for sl, _, _ in slots:
+            eng.release(sl)
         h2d = in_bytes + n_segs * 16
         d2h = (counts["out_bytes"] + 8 * counts["frames"] + 32 * counts["recs"] + 48 * counts["tcs"] + 24 * counts["usages"]
                + counts["text_bytes"] + 20 * counts["runs"] + 32 * n_segs + 64)
+        depth = 3
 
         def e2e_steps(k):
             inflight = []
@@ -291,7 +400,7 @@ def main():
                 eng.reset_all(0)
                 eng.submit(s2, n_segs, in_bytes)
                 inflight.append(s2)
-                if len(inflight) == N_SLOTS:
+                if len(inflight) == depth:
                     s_old = inflight.pop(0)
                     r = eng.collect(s_old)
                     frames += int(r.raw.n_frames)
@@ -302,10 +411,8 @@ def main():
                 eng.release(s_old)
             return frames
 
-        e2e_steps(N_SLOTS)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        e2e_steps(depth)
+        sync_all()
         k_e2e = max(4, min(args.steps, 12))
         t0 = time.perf_counter()
         fr = e2e_steps(k_e2e)
@@ -314,15 +421,15 @@ def main():
         e2e_s = sh.max_over_ranks(e2e_s, world)
         fr_all = sh.reduce_counters({"f": fr}, world)["f"]
         e2e = {"value": fr_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": k_e2e, "ms_per_step": 1e3 * e2e_s / k_e2e,
-               "path": f"sse_acquire/sse_submit/sse_collect/sse_release, {N_SLOTS} slots in flight, host buffers pinned"}
+               "steps": k_e2e, "ms_per_step": 1e3 * e2e_s / k_e2e, "h2d_gbs_per_rank": h2d / (e2e_s / k_e2e) / 1e9,
+               "path": f"sse_acquire/sse_submit/sse_collect/sse_release, {depth} slots in flight, host buffers pinned"}
 
     dev_ms = sh.max_over_ranks(dev_ms, world)
     tot = sh.reduce_counters(counts, world)
     chunks_per_step = tot["frames"]
     value = chunks_per_step * args.steps / (dev_ms / 1e3)
 
-    # ---- roofline of the stream kernel (rank 0's launch): algorithmic bytes / measured duration
+    # ---- roofline of the step (rank 0's launches): algorithmic bytes / measured duration
     # b_in read once + b_out delivered once + frame table + records (+ per-segment descriptors and state).
     # moved_bytes is what the zero-copy path really has to touch: frames that are spans of the input are never written.
     side = (8 * counts["frames"] + 32 * counts["recs"] + 48 * counts["tcs"] + 24 * counts["usages"] + counts["text_bytes"]
@@ -340,13 +447,13 @@ def main():
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if tj.get("workload") == args.workload and tj.get("streams") == args.streams and args.mode == 3 and not args.flags:
+        if tj.get("workload") == args.workload and tj.get("streams") == args.streams and args.mode in (None, 3) and not args.flags:
             traffic = tj.get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": "split pipeline: sse_stream_kernel<produce> + bucket sort (3 small kernels) + sse_decode_kernel + sse_finalize_kernel (whole step)",
+                "kernel": "sse_fused_kernel (+ sse_plan_kernel, 2 launches per step; the whole step is timed)",
                 "alg_bytes_per_launch": alg_bytes, "moved_bytes_per_launch": moved_bytes,
                 "zero_copy_frames": counts["zero_copy_frames"], "kernel_ms": 1e3 * kern_s,
                 "hbm_read_frac": counts["in_bytes"] / kern_s / 1e9 / peak}
@@ -355,21 +462,25 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {args.streams} concurrent mixed cohere/groq/anthropic/ollama streams per GPU incl. "
-                               "tool_calls deltas, mode R (MCP reframe + JSON side-band), every stream complete in one micro-batch",
-                   "streams_per_gpu": args.streams, "total_streams": args.streams * world,
+        "config": {"workload": workload_text(args), "streams_per_gpu": args.streams, "total_streams": args.streams * world,
+                   "batch": "every stream complete in one micro-batch (11 SSE events per stream and step)",
                    "sse_events_per_step": tot["events"], "chunks_emitted_per_step": tot["frames"],
                    "records_decoded_per_step": tot["recs"], "mean_event_bytes": tot["in_bytes"] / max(1, tot["events"]),
                    "input_bytes_per_step": tot["in_bytes"], "sharding": "hash(conn_id) % n_gpus, no collective",
-                   "l2": "working set (input + result tables > 350 MB per GPU) exceeds the 126 MB L2; no explicit flush",
-                   "streams_terminated": terminated, "records_json_ok": ok_recs},
+                   "l2": f"the timed steps rotate over {N_ROT} resident copies of the input ({in_payload / 1e6:.0f} MB each; L2 is 126 MB)",
+                   "streams_terminated": terminated, "records_json_ok": ok_recs,
+                   "parity": "bit-exact against oracle/ (C restatement of the Go path); parity unpinned against a Go run"},
         "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
     }
+    if segmented:
+        line["segmented"] = segmented
+    if strong:
+        line["c5_strong"] = strong
     if e2e:
         line["e2e"] = e2e
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         try:
-            line["cpu_baseline"] = cpu_baseline(bodies, mode, os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_baseline(bodies, mode, host_threads())
         except Exception as ex:  # the checker library is test infrastructure; report, do not hide
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
     if rank == 0:

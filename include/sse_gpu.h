@@ -70,6 +70,7 @@ typedef struct {
 #define SSE_FLAG_KERNEL_V1 1u  /* fused first-generation kernel (sequential per-lane decoder) */
 #define SSE_FLAG_KERNEL_V2 2u  /* fused producer/consumer kernel (table-driven automaton); default is the split pipeline */
 #define SSE_FLAG_KERNEL_SPLIT 4u /* round-1 split pipeline (produce / sort / decode / finalize kernels) */
+#define SSE_FLAG_NO_TEMPLATES 16u /* fused kernel: every line through the JSON automaton (no skeleton-template replay) */
 #define SSE_FLAG_COPY_OUT 8u   /* materialise every frame in the out arena. Default: a frame whose bytes already stand in the
                                   caller's input arena exactly as the reference would send them (every mode P line, and a mode R
                                   "data: ...\n" line followed by a blank line) is returned as a span of the input arena and is

@@ -72,6 +72,7 @@ struct KParams {
     uint4 *items_sorted;                           // items ordered by (length bucket, shape class): the 32 lanes of a decode batch walk alike lines
     // fused pipeline (plan -> fused tile kernel)
     uint2 *tiles;            uint32_t cap_tiles;   // {first segment, segment count} per tile
+    uint32_t *tcache;                              // skeleton templates kept between launches: [0] words used, [1..256] buckets, store
 };
 
 #ifdef __CUDACC__
@@ -89,4 +90,5 @@ int sse_v2_prepare(int device);                                                 
 int sse_launch_stream_kernel_v2(const KParams &p, void *stream, int sm_count, int device);
 int sse_fused_prepare(int device);                                                     // fused pipeline: tables + kernel attributes
 int sse_launch_fused(const KParams &p, void *stream, int sm_count, int device);        // plan kernel + fused tile kernel
-uint32_t sse_fused_max_line(void);                                                     // longest carry_slot_bytes the fused kernel supports
+uint32_t sse_fused_max_line(void);
+uint32_t sse_fused_tcache_words(void);                                                 // size of KParams.tcache                                                     // longest carry_slot_bytes the fused kernel supports

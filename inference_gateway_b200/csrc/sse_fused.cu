@@ -32,13 +32,18 @@ using namespace ssetab;
 
 constexpr int F_THREADS = 512;
 constexpr int F_WARPS = F_THREADS / 32;
-constexpr uint32_t TILE = 65536;
+constexpr uint32_t TILE = 53248;
 constexpr uint32_t TILE_PAD = 64;
 constexpr uint32_t BM_WORDS = TILE / 32;
 constexpr int MAX_TSEGS = 128;
 constexpr int LCAP = F_THREADS;            // lines per round: one thread per line
-constexpr int N_SHAPES = 128;              // shape key of a line to decode: number of stop bytes (quotes, mostly) in its payload
-constexpr int PLAN_GROUP = 1024;           // segments packed into tiles by one warp of the plan kernel
+constexpr int PLAN_GROUP = 1024;
+constexpr int TS_WORDS = 4096;             // template store (32-bit words)
+constexpr int NREC = 8, REC_MAX = 40;      // lanes recording a template at the same time; wildcards per template
+constexpr int JQ_CAP = 96;
+struct FJob { uint32_t s, e, dst, pad; uint32_t *patch; };
+struct FRecEv { uint16_t start, len; uint8_t kind, op; };
+struct FRec { uint16_t n, nonsimple, n_str, n_arr; FRecEv ev[REC_MAX]; };           // segments packed into tiles by one warp of the plan kernel
 
 // ---------------------------------------------------------------- tables (global -> shared at kernel start)
 constexpr int HASH_BITS = 7;
@@ -83,19 +88,31 @@ struct FSmem {
     uint16_t matlist[LCAP];                // lines of the round whose bytes have to be materialised
     FSeg seg[MAX_TSEGS];
     FTables T;
+    uint32_t tstore[TS_WORDS];             // skeleton templates of this CTA (kept for the whole launch)
+    uint32_t thead[256];                   // bucket (clean stop count) -> newest template
+    FRec rec[NREC];
+    uint32_t ts_used, rec_busy, build_lock;
+    FJob jq[JQ_CAP];                       // strings of this round that need unquoting
+    uint32_t jq_n;
     alignas(8) unsigned long long mbar;
     uint32_t scan_a[F_WARPS], scan_b[F_WARPS];
-    uint32_t hist[N_SHAPES];               // decode jobs per shape key (counting sort of a round's jobs)
     uint32_t bc[16];
     long long prof_t;
 };
 static_assert(sizeof(FSmem) <= 113 * 1024, "two CTAs per SM");
 
 #ifdef SSE_PROF
-__device__ unsigned long long g_prof[16];
+__device__ unsigned long long g_prof[160];
 #define PROF(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_prof[i], (unsigned long long)(t_ - S.prof_t)); S.prof_t = t_; } } while (0)
 #else
 #define PROF(i) do { } while (0)
+#endif
+#ifdef SSE_PROF
+#define PCOUNT(i, n) atomicAdd(&g_prof[i], (unsigned long long)(n))
+#define PSTAMP(k) do { __syncwarp(); if ((threadIdx.x & 31u) == 0) { const long long t_ = clock64(); atomicAdd(&g_prof[64 + (k) * 16 + (threadIdx.x >> 5)], (unsigned long long)(t_ - ts_)); ts_ = t_; } } while (0)
+#else
+#define PSTAMP(k) do { } while (0)
+#define PCOUNT(i, n) do { } while (0)
 #endif
 
 // ---------------------------------------------------------------- bulk copy + mbarrier (PTX)
@@ -227,6 +244,65 @@ __device__ __forceinline__ uint32_t count_stops(const FSmem &S, uint32_t a, uint
     return n + __popc(bits);
 }
 
+// Warp-cooperative unquote of a validated string body (decode.go unquoteBytes): 32 bytes per step. Plain bytes and the
+// two-byte escapes (\" \\ \/ \b \f \n \r \t) are placed in parallel -- an escaping backslash is one that is preceded by an
+// even number of backslashes; \uXXXX and non-ASCII bytes (kept, or U+FFFD when invalid) are done by lane 0 one at a time.
+__device__ __noinline__ void warp_unquote2(const uint8_t *__restrict__ src, uint32_t s, uint32_t e, uint8_t *__restrict__ dst, uint32_t *patch) {
+    const uint32_t lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t i = s, n = 0;
+    while (i < e) {
+        const uint32_t idx = i + lane;
+        const bool valid = idx < e;
+        const uint32_t c = valid ? (uint32_t)src[idx] : 0x20u;
+        const uint32_t nvalid = min(32u, e - i);
+        const unsigned bs = __ballot_sync(FULL, valid && c == '\\');
+        const unsigned hi = __ballot_sync(FULL, valid && c >= 0x80u);
+        const uint32_t below = lane ? (bs << (32u - lane)) : 0u;
+        const uint32_t run = (uint32_t)__clz((int)~below);                // consecutive backslashes right before this byte
+        const bool escaped = (run & 1u) != 0;                         // the character an escaping backslash introduces
+        const bool escaping = ((bs >> lane) & 1u) && !escaped;
+        const unsigned um = __ballot_sync(FULL, valid && escaped && c == 'u');
+        const unsigned em = __ballot_sync(FULL, escaping);
+        uint32_t limit = nvalid;
+        if (hi) limit = min(limit, (uint32_t)__ffs(hi) - 1u);
+        if (um) limit = min(limit, (uint32_t)__ffs(um) - 2u);         // stop at the backslash of \uXXXX
+        if (limit && ((em >> (limit - 1u)) & 1u)) limit--;            // an escape cut by the window: leave its backslash for the next step
+        if (limit) {
+            uint32_t m = c;
+            if (escaped) m = c == 'b' ? 8u : c == 'f' ? 12u : c == 'n' ? 10u : c == 'r' ? 13u : c == 't' ? 9u : c;
+            const bool outp = lane < limit && !escaping;
+            const unsigned om = __ballot_sync(FULL, outp);
+            if (outp) dst[n + __popc(om & lt)] = (uint8_t)m;
+            n += __popc(om); i += limit;
+            continue;
+        }
+        uint32_t ni = i, nn = n;                                      // one \uXXXX (pair) or one non-ASCII sequence
+        if (lane == 0) {
+            const uint32_t c0 = src[i];
+            if (c0 == '\\') {
+                ni = i + 2;
+                uint32_t r = (uint32_t)hex4(src + ni);
+                ni += 4;
+                if (r >= 0xD800 && r < 0xE000) {
+                    int r1 = -1;
+                    if (ni + 6 <= e && src[ni] == '\\' && src[ni + 1] == 'u') r1 = hex4(src + ni + 2);
+                    if (r < 0xDC00 && r1 >= 0xDC00 && r1 < 0xE000) { r = 0x10000 + ((r - 0xD800) << 10) + ((uint32_t)r1 - 0xDC00); ni += 6; }
+                    else r = 0xFFFD;
+                }
+                nn += put_rune(dst, nn, r);
+            } else {
+                const int k = utf8_valid_len(src + i, (int)(e - i));
+                if (k == 0) { nn += put_rune(dst, nn, 0xFFFD); ni = i + 1; }
+                else { for (int q = 0; q < k; q++) dst[nn + q] = src[i + q]; nn += k; ni = i + k; }
+            }
+        }
+        i = __shfl_sync(FULL, ni, 0); n = __shfl_sync(FULL, nn, 0);
+    }
+    if (lane == 0) *patch = n;
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------- stage 2: the decoder
 // One lane per line. The lane state lives in registers: everything that touches it is inlined, the helpers that stay
 // out of line take scalars. The walk is the byte automaton of sse_tables.h with shortcuts that are, by construction,
@@ -245,9 +321,19 @@ struct FLane {
     unsigned long long ct, ct1, sstk;
     uint32_t content_pos, content_len, tc_count, tc_first, tc_prev, tc_cur, tcb, usage_idx;
     uint32_t rec, delta, plen, line;
-    uint32_t js, je, jdst; uint32_t *jpatch;     // one deferred unquote job (warp-cooperative)
+    uint32_t rslot;                              // recording a template into S.rec[rslot] (SSE_NONE: no)
     bool busy;
 };
+
+enum : uint8_t { WK_END = 0, WK_STR = 1, WK_INT = 2 };      // template wildcards (see "skeleton templates" below)
+enum : uint8_t { OP_NONE = 0, OP_CONTENT, OP_FINISH, OP_TC_ID, OP_TC_TYPE, OP_TC_NAME, OP_TC_ARGS, OP_TC_INDEX,
+                 OP_U_PROMPT, OP_U_COMPLETION, OP_U_TOTAL, OP_CHK_I64, OP_CHK_F32 };
+__device__ __forceinline__ void rec_event(FSmem &S, FLane &L, uint32_t kind, uint32_t start, uint32_t len, uint32_t op) {
+    FRec &R = S.rec[L.rslot];
+    if (R.n < REC_MAX) { FRecEv e; e.start = (uint16_t)start; e.len = (uint16_t)len; e.kind = (uint8_t)kind; e.op = (uint8_t)op; R.ev[R.n] = e; R.n++; }
+    else R.nonsimple = 1;
+}
+__device__ __forceinline__ void rec_nonsimple(FSmem &S, FLane &L) { if (L.rslot != SSE_NONE) S.rec[L.rslot].nonsimple = 1; }
 
 __device__ __forceinline__ bool fl_live(const FLane &L) { return L.sd >= 3 && ((L.sstk >> 10) & 31ull) == N_CHOICE && L.choices_count == 1; }
 __device__ __forceinline__ uint32_t fl_top(const FLane &L) { return (uint32_t)((L.sstk >> (5 * (L.sd - 1))) & 31ull); }
@@ -274,10 +360,14 @@ __device__ __forceinline__ Span f_capture(const KParams &P, FSmem &S, FLane &L, 
     const uint32_t o = f_text_alloc(P, (((dec & 2u) ? 3u * len : len) + 3u) & ~3u);
     if (o == SSE_NONE) return r;
     r.off = o;
-    if (patch && L.jpatch == nullptr) {
-        L.js = s; L.je = s + len; L.jdst = o; L.jpatch = patch;
-        r.len = len;          // patched when the warp drains the job; raw > 0 implies decoded > 0
-        return r;
+    if (patch) {              // decoded after the lines are through, one warp per string (process_window)
+        const uint32_t qi = atomicAdd(&S.jq_n, 1u);
+        if (qi < (uint32_t)JQ_CAP) {
+            FJob jb; jb.s = s; jb.e = s + len; jb.dst = o; jb.patch = patch;
+            S.jq[qi] = jb;
+            r.len = len;      // patched by the job; raw > 0 implies decoded > 0
+            return r;
+        }
     }
     r.len = json_unquote_write(S.tile, (int)s, (int)(s + len), P.text + o);
     return r;
@@ -328,14 +418,19 @@ __device__ __forceinline__ void f_drop_tcs(FLane &L) {
     L.sf &= ~(SF_TCNONNIL | SF_TCOPEN | SF_TCVALID);
     L.tc_count = 0; L.tc_first = L.tc_prev = L.tc_cur = SSE_NONE; L.tcb = 0;
 }
-__device__ __forceinline__ void f_cancel_job(FLane &L, uint32_t *patch) { if (L.jpatch == patch) L.jpatch = nullptr; }
+// a span is overwritten (repeated key, null): a queued unquote job must not patch its length later
+__device__ __noinline__ void f_cancel_job(FSmem &S, uint32_t *patch) {
+    const uint32_t n = min(S.jq_n, (uint32_t)JQ_CAP);
+    for (uint32_t i = 0; i < n; i++) if (S.jq[i].patch == patch) S.jq[i].patch = nullptr;
+}
 
-__device__ __forceinline__ void f_null(const KParams &P, FLane &L) {
+__device__ __forceinline__ void f_null(const KParams &P, FSmem &S, FLane &L) {
     const uint32_t ty = L.cur & 15u, tgt = (L.cur >> 9) & 15u;
     if (ty == TY_TS) { L.sf &= ~SF_GBAD; return; }
     if (tgt == TG_NONE || tgt == TG_FINISH || tgt == TG_CONTENT || tgt == TG_PROMPT || tgt == TG_COMPLETION || tgt == TG_TOTAL ||
         tgt == TG_TC_INDEX || tgt == TG_NAME || tgt == TG_ARGS) return;      // null leaves non-pointer fields untouched
     const bool tco = (L.sf & SF_TCOPEN) && fl_live(L) && L.tc_cur != SSE_NONE;
+    if (tgt != TG_USAGE || L.usage_idx != SSE_NONE) rec_nonsimple(S, L);     // a reset is not something a template replays
     switch (tgt) {
     case TG_CHOICES:
         L.n_choices = 0; L.choices_count = 0; L.finish = SSE_FIN_NONE; L.content_pos = L.content_len = 0;
@@ -345,15 +440,15 @@ __device__ __forceinline__ void f_null(const KParams &P, FLane &L) {
     case TG_USAGE: L.sf &= ~SF_USAGE; L.usage_idx = SSE_NONE; break;
     case TG_TOOLCALLS: if (fl_live(L)) f_drop_tcs(L); break;
     case TG_TC_ID:
-        if ((L.sf & SF_TCOPEN) && fl_live(L)) { L.tcb &= ~(SSE_TC_HAS_ID | SSE_TC_ID_TEXT); if (tco) { sse_tc *t = &P.tcs[L.tc_cur]; f_cancel_job(L, &t->id_len); t->id_off = t->id_len = 0; } }
+        if ((L.sf & SF_TCOPEN) && fl_live(L)) { L.tcb &= ~(SSE_TC_HAS_ID | SSE_TC_ID_TEXT); if (tco) { sse_tc *t = &P.tcs[L.tc_cur]; f_cancel_job(S, &t->id_len); t->id_off = t->id_len = 0; } }
         break;
     case TG_TC_TYPE:
-        if ((L.sf & SF_TCOPEN) && fl_live(L)) { L.tcb &= ~(SSE_TC_HAS_TYPE | SSE_TC_TYPE_TEXT); if (tco) { sse_tc *t = &P.tcs[L.tc_cur]; f_cancel_job(L, &t->type_len); t->type_off = t->type_len = 0; } }
+        if ((L.sf & SF_TCOPEN) && fl_live(L)) { L.tcb &= ~(SSE_TC_HAS_TYPE | SSE_TC_TYPE_TEXT); if (tco) { sse_tc *t = &P.tcs[L.tc_cur]; f_cancel_job(S, &t->type_len); t->type_off = t->type_len = 0; } }
         break;
     case TG_TC_FUNCTION:
         if ((L.sf & SF_TCOPEN) && fl_live(L)) {
             L.tcb &= ~(SSE_TC_HAS_FUNC | SSE_TC_NAME_TEXT | SSE_TC_ARGS_TEXT | TCB_NAME | TCB_ARGS);
-            if (tco) { sse_tc *t = &P.tcs[L.tc_cur]; f_cancel_job(L, &t->name_len); f_cancel_job(L, &t->args_len); t->name_off = t->name_len = t->args_off = t->args_len = 0; }
+            if (tco) { sse_tc *t = &P.tcs[L.tc_cur]; f_cancel_job(S, &t->name_len); f_cancel_job(S, &t->args_len); t->name_off = t->name_len = t->args_off = t->args_len = 0; }
         }
         break;
     default: break;
@@ -447,7 +542,8 @@ __device__ __noinline__ uint32_t f_match_finish(const FSmem &S, uint32_t s, uint
 }
 
 // ---- the semantic actions (decode.go object / array / literalStore against the struct types)
-__device__ __forceinline__ void f_open(const KParams &P, FLane &L, bool arr) {
+__device__ __forceinline__ void f_open(const KParams &P, FSmem &S, FLane &L, bool arr) {
+    if (L.rslot != SSE_NONE && arr) S.rec[L.rslot].n_arr++;
     if (L.depth >= 128) { L.sf |= SF_DEPTH | SF_SYN; L.p = L.pe - 1; L.st = S_END; return; }
     if (L.depth < 64) L.ct = (L.ct & ~(1ull << L.depth)) | ((unsigned long long)arr << L.depth);
     else L.ct1 = (L.ct1 & ~(1ull << (L.depth - 64))) | ((unsigned long long)arr << (L.depth - 64));
@@ -469,8 +565,8 @@ __device__ __forceinline__ void f_open(const KParams &P, FLane &L, bool arr) {
                     if (L.usage_idx == SSE_NONE) L.usage_idx = f_usage_alloc(P);
                 }
                 else if (tgt == TG_TC_FUNCTION) { if (live && (L.sf & SF_TCOPEN)) L.tcb |= SSE_TC_HAS_FUNC; }
-                else if (tgt == TG_CHOICES) L.choices_count = 0;
-                else if (tgt == TG_TOOLCALLS) { if (live) { f_drop_tcs(L); L.sf |= SF_TCNONNIL; } }
+                else if (tgt == TG_CHOICES) { if (L.n_choices || L.choices_count) rec_nonsimple(S, L); L.choices_count = 0; }
+                else if (tgt == TG_TOOLCALLS) { if (live) { if (L.sf & SF_TCNONNIL) rec_nonsimple(S, L); f_drop_tcs(L); L.sf |= SF_TCNONNIL; } }
             }
             if (sub == N_GOOGLE) L.sf &= ~SF_GBAD;
         }
@@ -498,16 +594,19 @@ __device__ __forceinline__ void f_key_end(FSmem &S, FLane &L, uint32_t start, ui
     }
     L.cur = cur;
     L.st = S_COLON;
+    if (L.rslot != SSE_NONE) S.rec[L.rslot].n_str++;
 }
 // a string value [start, start+len) ended; d2: bit 0 escapes, bit 1 invalid UTF-8
 __device__ __forceinline__ void f_vstr_end(const KParams &P, FSmem &S, FLane &L, uint32_t start, uint32_t len, uint32_t d2) {
     const uint32_t ty = L.cur & 15u, tgt = (L.cur >> 9) & 15u;
+    uint32_t op = OP_NONE;
     if (ty == TY_STR || ty == TY_PSTR) {
         if (tgt != TG_NONE && fl_live(L)) {
             if (tgt == TG_CONTENT) {
+                op = OP_CONTENT;
                 L.content_pos = start; L.content_len = len;
                 L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | SF_CSET | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
-            } else if (tgt == TG_FINISH) L.finish = f_match_finish(S, start, len, d2);
+            } else if (tgt == TG_FINISH) { L.finish = f_match_finish(S, start, len, d2); op = OP_FINISH; }
             else if (L.sf & SF_TCOPEN) {
                 // the four strings of a tool-call element share one code path: field k of {id, type, name, arguments}
                 const uint32_t k = tgt == TG_TC_ID ? 0u : tgt == TG_TC_TYPE ? 1u : tgt == TG_NAME ? 2u : tgt == TG_ARGS ? 3u : 4u;
@@ -517,9 +616,10 @@ __device__ __forceinline__ void f_vstr_end(const KParams &P, FSmem &S, FLane &L,
                     if (k == 0) L.tcb |= SSE_TC_HAS_ID; else if (k == 1) L.tcb |= SSE_TC_HAS_TYPE;
                     else if (k == 2) L.tcb = (L.tcb & ~TCB_NAME) | (len ? TCB_NAME : 0u);
                     else L.tcb = (L.tcb & ~TCB_ARGS) | (len ? TCB_ARGS : 0u);
+                    if (L.tc_cur != SSE_NONE && L.tc_count <= 16u) op = (OP_TC_ID + k) | ((L.tc_count - 1u) << 4); else rec_nonsimple(S, L);
                     if (L.tc_cur != SSE_NONE) {
                         uint32_t *span = &P.tcs[L.tc_cur].id_off + 2u * k;     // {off, len} pairs are laid out in this order
-                        f_cancel_job(L, span + 1);
+                        f_cancel_job(S, span + 1);
                         const Span sp = f_capture(P, S, L, start, len, d2, span + 1);
                         span[0] = sp.off; span[1] = sp.len;
                         if (sp.text) L.tcb |= text_bit;
@@ -530,10 +630,20 @@ __device__ __forceinline__ void f_vstr_end(const KParams &P, FSmem &S, FLane &L,
     } else if (ty == TY_TS) L.sf &= ~SF_GBAD;
     else if (ty != TY_SKIP) L.sf |= SF_TYPE;
     fl_value_done(L);
+    if (L.rslot != SSE_NONE) { S.rec[L.rslot].n_str++; rec_event(S, L, WK_STR, start, len, op); }
 }
 // a number [start, end) ended
 __device__ __forceinline__ void f_number_end(const KParams &P, FSmem &S, FLane &L, uint32_t start, uint32_t end, bool is_int) {
     const uint32_t ty = L.cur & 15u, tgt = (L.cur >> 9) & 15u;
+    if (L.rslot != SSE_NONE && is_int) {
+        uint32_t op = OP_NONE;
+        if (ty == TY_INT) {
+            op = OP_CHK_I64;
+            if (L.usage_idx != SSE_NONE && (tgt == TG_PROMPT || tgt == TG_COMPLETION || tgt == TG_TOTAL)) op = OP_U_PROMPT + (tgt - TG_PROMPT);
+            else if (tgt == TG_TC_INDEX && (L.sf & SF_TCOPEN) && fl_live(L) && L.tc_cur != SSE_NONE && L.tc_count <= 16u) op = OP_TC_INDEX | ((L.tc_count - 1u) << 4);
+        } else if (ty == TY_F32) op = OP_CHK_F32;
+        rec_event(S, L, WK_INT, start, end - start, op);
+    }
     if (ty == TY_INT) {
         if (!is_int) L.sf |= SF_TYPE;
         else if (end - start > 18 || tgt != TG_NONE)
@@ -547,8 +657,8 @@ __device__ __forceinline__ void f_number_end(const KParams &P, FSmem &S, FLane &
 // returns true when the current byte has to be looked up again in the new state
 __device__ __forceinline__ bool f_action(const KParams &P, FSmem &S, FLane &L, uint32_t t) {
     switch (t) {
-    case A_OPEN_OBJ: f_open(P, L, false); return false;
-    case A_OPEN_ARR: f_open(P, L, true); return false;
+    case A_OPEN_OBJ: f_open(P, S, L, false); return false;
+    case A_OPEN_ARR: f_open(P, S, L, true); return false;
     case A_CLOSE_OBJ: case A_CLOSE_ARR: f_close(P, L); return false;
     case A_KEY_END: f_key_end(S, L, L.p - L.slen, L.slen, (L.sf & (SF_ESC | SF_HI)) != 0); return false;
     case A_VSTR_END: f_vstr_end(P, S, L, L.p - L.slen, L.slen, ((L.sf & SF_ESC) ? 1u : 0u) | ((L.sf & SF_BAD) ? 2u : 0u)); return false;
@@ -561,7 +671,7 @@ __device__ __forceinline__ bool f_action(const KParams &P, FSmem &S, FLane &L, u
         fl_value_done(L);
         return false;
     }
-    case A_LIT_NULL: f_null(P, L); fl_value_done(L); return false;
+    case A_LIT_NULL: f_null(P, S, L); fl_value_done(L); return false;
     case A_ELEM_REDO: f_elem_begin(P, L); L.st = S_VAL; return true;
     case A_COMMA_ARR: f_elem_begin(P, L); L.st = S_VAL; return false;
     default:   // A_ERR
@@ -684,7 +794,7 @@ value:
                 }
             }
         } else if (c == 'n' && L.p + 4u <= L.pe && load4(S, L.p) == 0x6C6C756Eu) {
-            f_null(P, L); fl_value_done(L);
+            f_null(P, S, L); fl_value_done(L);
             L.p += 4u;
             goto after_value;
         }
@@ -696,6 +806,225 @@ value:
 after_value:
     if (L.st == S_AFTO && L.p < L.pe && S.tile[L.p] == ',') { L.st = S_KEY; L.p++; }
 }
+// ---------------------------------------------------------------- skeleton templates
+// Consecutive chunks of a stream -- and the chunks of every other stream of the same provider -- differ only inside string
+// values and integers: keys, punctuation, literals are byte for byte the same. A line parsed by the automaton above leaves a
+// template in the CTA's cache: its bytes outside those wildcards (the skeleton) and, per wildcard, what the parse did with
+// it (capture op). A later line whose skeleton compares equal, and whose wildcards are again a well-formed string body /
+// an integer, takes the automaton through exactly the same transitions -- so its record is the template's with its own
+// spans, and the automaton does not have to run. The compare-and-scan loop is the same code for every template: the lanes
+// of a warp stay together whatever mix of lines they hold. Lines that match no template take the automaton (and record one).
+constexpr uint32_t T_LIT_MAX = 1024;       // skeleton bytes per template
+constexpr uint32_t TF_HAS_USAGE = 1, TF_SIMPLE = 2;   // TF_SIMPLE: only content / finish_reason / range-check ops: no second walk
+constexpr uint32_t T_HDR = 6;                           // header words
+// template in the store: [0] next | key << 16   [1] skeleton bytes | flags << 16 | tc_count << 24   [2] static record flags
+// [3] n_choices | n_items << 16   [4] the last (up to 4) bytes of the skeleton   [5] their mask, then n_items items (lit_len | kind << 16 | op << 24), then 4 words of per-element tool-call flags when
+// tc_count > 0, then the skeleton runs (each starts on a word).
+
+// body of a string value from fp (just behind the opening quote): position of the closing quote, or SSE_NONE when the
+// body is not well formed (control byte, bad escape, no closing quote). d2 / done as the automaton would have them.
+__device__ __forceinline__ uint32_t t_scan_string(const FSmem &S, uint32_t fp, uint32_t pe, bool rmode, uint32_t &d2, bool &done) {
+    uint32_t p = fp;
+    for (;;) {
+        const uint32_t q = next_stop(S, p, pe);
+        if (q >= pe) return SSE_NONE;
+        const uint32_t c = S.tile[q];
+        if (c == '"') return q;
+        uint32_t adv = 0;
+        if (c == '\\') {
+            const uint32_t c2 = S.tile[q + 1u];
+            if (q + 2u <= pe && (c2 == '"' || c2 == '\\' || c2 == '/' || c2 == 'b' || c2 == 'f' || c2 == 'n' || c2 == 'r' || c2 == 't')) adv = 2;
+            else if (c2 == 'u' && q + 6u <= pe && hex4(S.tile + q + 2u) >= 0) adv = 6;
+            if (!adv) return SSE_NONE;
+            d2 |= 1u;
+        } else if (c == '[') {
+            if (rmode && q + 6u <= pe && is_done_at(S.tile + q)) done = true;
+            adv = 1;
+        } else if (c >= 0x80u) {
+            adv = (uint32_t)utf8_valid_len(S.tile + q, (int)(pe - q));
+            if (!adv) { adv = 1; d2 |= 2u; }        // invalid UTF-8: the automaton flags it (A_BAD_*) and goes on byte by byte
+        } else return SSE_NONE;                     // control byte
+        p = q + adv;
+        if (p >= pe) return SSE_NONE;
+    }
+}
+// integer from fp: [-] 0 | [1-9][0-9]*; returns its end, or SSE_NONE
+__device__ __forceinline__ uint32_t t_scan_int(const FSmem &S, uint32_t fp, uint32_t pe) {
+    uint32_t i = fp;
+    if (i < pe && S.tile[i] == '-') i++;
+    if (i >= pe) return SSE_NONE;
+    const uint32_t d0 = S.tile[i];
+    if (d0 == '0') return i + 1u;
+    if (d0 - '1' > 8u) return SSE_NONE;
+    i++;
+    while (i + 4u <= pe && nondigit4(load4(S, i)) == 0) i += 4u;
+    while (i < pe && (uint32_t)S.tile[i] - '0' <= 9u) i++;
+    return i;
+}
+
+// Walk the line [ps, pe) along template T. APPLY = false: compare the skeleton and scan the wildcards, no side effects;
+// true: (after a successful compare) run the capture ops into the lane state. Returns false when the line does not fit.
+// SYNC: every lane of the warp is in the call (act: this lane has a line and a template); the lanes then meet after every
+// item -- without that, lanes that hold different templates drift apart and the warp executes them one after the other.
+template <bool APPLY, bool SYNC>
+__device__ __forceinline__ bool t_walk(const KParams &P, FSmem &S, FLane &L, const uint32_t *T, uint32_t ps, uint32_t pe,
+                                       uint32_t tc_base, uint32_t &tc_dyn, bool act = true) {
+    const uint32_t n_items = act ? T[3] >> 16 : 0u, tc_count = act ? T[1] >> 24 : 0u;
+    const uint32_t *items = T + T_HDR;
+    const uint32_t *lw = items + n_items + (tc_count ? 4u : 0u);
+    const bool rmode = (L.sf & SF_RMODE) != 0;
+    uint32_t fp = ps;
+    bool done = false, ok = act;
+    if (!APPLY && act) { L.content_pos = L.content_len = 0; L.finish = SSE_FIN_NONE; L.sf &= ~(SF_CDEC | SF_CBAD); }   // captures of an earlier candidate
+    for (uint32_t i = 0; ; i++) {
+        const bool go = ok && i < n_items;
+        if (SYNC) { if (!__any_sync(FULL, go)) break; } else if (!go) break;
+        if (go) {
+        const uint32_t it = items[i];
+        const uint32_t lit = it & 0xFFFFu, kind = (it >> 16) & 0xFFu, op = it >> 24;
+        if (!APPLY) {
+            uint32_t diff = fp + lit > pe ? 1u : 0u;
+            if (!diff) {
+                uint32_t j = 0;
+                for (; j + 4u <= lit; j += 4u) diff |= load4(S, fp + j) ^ lw[j >> 2];
+                if (j < lit) diff |= (load4(S, fp + j) ^ lw[j >> 2]) & ((1u << ((lit - j) * 8u)) - 1u);
+            }
+            if (diff) ok = false;
+        }
+        fp += lit; lw += (lit + 3u) >> 2;
+        if (kind == WK_END) { if (!APPLY && fp != pe) ok = false; }
+        else if (ok) {
+            uint32_t end, d2 = 0;
+            if (kind == WK_STR) end = t_scan_string(S, fp, pe, rmode, d2, done);
+            else end = t_scan_int(S, fp, pe);
+            if (end == SSE_NONE) ok = false;
+            else {
+                if (!APPLY && op != OP_NONE) {        // register-only captures are taken while comparing (TF_SIMPLE templates)
+                    const uint32_t code = op & 15u, len = end - fp;
+                    if (code == OP_CONTENT) {
+                        L.content_pos = fp; L.content_len = len;
+                        L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
+                    } else if (code == OP_FINISH) L.finish = f_match_finish(S, fp, len, d2);
+                    else if ((code == OP_CHK_I64 || code == OP_CHK_F32) && len > 18u) tc_dyn |= 0x80000000u;   // needs the range check of t_apply
+                }
+                if (APPLY && op != OP_NONE) {
+                    const uint32_t code = op & 15u, ord = op >> 4, len = end - fp;
+                    switch (code) {
+                    case OP_CONTENT:
+                        L.content_pos = fp; L.content_len = len;
+                        L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
+                        break;
+                    case OP_FINISH: L.finish = f_match_finish(S, fp, len, d2); break;
+                    case OP_TC_ID: case OP_TC_TYPE: case OP_TC_NAME: case OP_TC_ARGS:
+                        if (tc_base != SSE_NONE) {
+                            const uint32_t k = code - OP_TC_ID;
+                            sse_tc *t = &P.tcs[tc_base + ord];
+                            uint32_t *span = &t->id_off + 2u * k;
+                            f_cancel_job(S, span + 1);
+                            const Span sp = f_capture(P, S, L, fp, len, d2, span + 1);
+                            span[0] = sp.off; span[1] = sp.len;
+                            const uint32_t text_bit = SSE_TC_ID_TEXT << k;
+                            t->flags = (t->flags & ~text_bit) | (sp.text ? text_bit : 0u);
+                            if (k >= 2u) { const uint32_t b = 1u << (2u * ord + (k - 2u)); tc_dyn = len ? (tc_dyn | b) : (tc_dyn & ~b); }
+                        }
+                        break;
+                    case OP_TC_INDEX:
+                        L.sf |= f_number_value(P, S.tile, TY_INT, TG_TC_INDEX, fp, end, SSE_NONE, tc_base != SSE_NONE ? tc_base + ord : SSE_NONE);
+                        break;
+                    case OP_U_PROMPT: L.sf |= f_number_value(P, S.tile, TY_INT, TG_PROMPT, fp, end, L.usage_idx, SSE_NONE); break;
+                    case OP_U_COMPLETION: L.sf |= f_number_value(P, S.tile, TY_INT, TG_COMPLETION, fp, end, L.usage_idx, SSE_NONE); break;
+                    case OP_U_TOTAL: L.sf |= f_number_value(P, S.tile, TY_INT, TG_TOTAL, fp, end, L.usage_idx, SSE_NONE); break;
+                    case OP_CHK_I64: if (len > 18u) L.sf |= f_number_value(P, S.tile, TY_INT, TG_NONE, fp, end, SSE_NONE, SSE_NONE); break;
+                    case OP_CHK_F32: L.sf |= f_number_value(P, S.tile, TY_F32, TG_NONE, fp, end, SSE_NONE, SSE_NONE); break;
+                    default: break;
+                    }
+                }
+                fp = end;
+            }
+        }
+        }
+        if (SYNC) __syncwarp();
+    }
+    if (APPLY && done) L.sf |= SF_DONELINE;
+    if (!APPLY && done) tc_dyn |= 0x40000000u;
+    return ok;
+}
+
+__device__ __noinline__ uint32_t f_tcs_alloc(const KParams &P, uint32_t n, const uint32_t *static_flags) {
+    const uint32_t base = atomicAdd(&P.ctr->n_tcs, n);
+    if (base + n > P.cap_tcs) { sse_overflow(P.ctr, SSE_OVF_TCS); return SSE_NONE; }
+    const uint8_t *sf8 = reinterpret_cast<const uint8_t *>(static_flags);
+    for (uint32_t j = 0; j < n; j++) {
+        uint4 *q = reinterpret_cast<uint4 *>(&P.tcs[base + j]);
+        q[0] = make_uint4(0u, 0u, (uint32_t)sf8[j], j + 1u < n ? base + j + 1u : SSE_NONE);
+        q[1] = make_uint4(0u, 0u, 0u, 0u); q[2] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    return base;
+}
+
+// number of stop bytes the line would have if its strings were clean: 2 per string + '[' outside strings; SSE_NONE if a
+// string does not end
+__device__ __noinline__ uint32_t t_clean_key(const FSmem &S, uint32_t ps, uint32_t pe) {
+    uint32_t p = ps, n = 0;
+    bool in_str = false;
+    while (p < pe) {
+        const uint32_t q = next_stop(S, p, pe);
+        if (q >= pe) break;
+        const uint32_t c = S.tile[q];
+        p = q + 1u;
+        if (in_str) {
+            if (c == '"') { in_str = false; n += 2u; }
+            else if (c == '\\') p = q + 2u;
+        } else if (c == '"') in_str = true;
+        else if (c == '[') n++;
+    }
+    return in_str ? SSE_NONE : n;
+}
+
+// The record of a retired line (agent.go:205-242 reads) from the lane's final state. Out of line: called from the template
+// path and from the automaton.
+__device__ __noinline__ void f_emit_record(const KParams &P, FSmem &S, uint32_t sf, uint32_t n_choices, uint32_t usage_idx, uint32_t content_pos,
+                                           uint32_t content_len, uint32_t finish, uint32_t tc_count, uint32_t tc_first, uint32_t rec,
+                                           uint32_t plen, uint32_t line, uint32_t delta) {
+    sse_rec r;
+    r.frame = SSE_NONE; r.flags = 0; r.content_off = r.content_len = 0; r.tc_first = SSE_NONE; r.tc_count = 0; r.n_choices = 0;
+    r.usage = SSE_NONE;
+    if (sf & SF_DEPTH) r.flags |= SSE_F_DEPTH_LIMIT;
+    if (sf & SF_DONELINE) r.flags |= SSE_F_DONE_LINE;      // swallowed by the reframe, parsed for agent.go:377-402
+    bool terminates = false;
+    if (!(sf & (SF_SYN | SF_TYPE))) {
+        r.flags |= SSE_F_JSON_OK;
+        r.n_choices = (uint16_t)min(n_choices, 0xFFFFu);
+        if ((sf & SF_USAGE) && usage_idx != SSE_NONE) { r.usage = usage_idx; r.flags |= SSE_F_HAS_USAGE; }
+        if (n_choices > 0) {
+            FLane C; C.delta = delta;
+            const Span ct = f_capture(P, S, C, content_pos, content_len, ((sf & SF_CDEC) ? 1u : 0u) | ((sf & SF_CBAD) ? 2u : 0u),
+                                      &P.recs[rec].content_len);
+            r.content_off = ct.len ? ct.off : 0; r.content_len = ct.len;
+            if (ct.text && ct.len) r.flags |= SSE_F_CONTENT_TEXT;
+            r.flags |= finish << SSE_F_FINISH_SHIFT;
+            if (sf & SF_TCNONNIL) r.flags |= SSE_F_TC_NONNIL;
+            if (sf & SF_TCVALID) r.flags |= SSE_F_TC_VALID;
+            r.tc_first = tc_count ? tc_first : SSE_NONE;
+            r.tc_count = (uint16_t)min(tc_count, 0xFFFFu);
+            if ((sf & SF_RMODE) && !(sf & SF_DONELINE) && (finish == SSE_FIN_STOP || finish == SSE_FIN_TOOL_CALLS)) {
+                r.flags |= SSE_F_TERMINATES;
+                terminates = true;
+            }
+        }
+    }
+    r.payload_len = plen;
+    uint4 *q = reinterpret_cast<uint4 *>(&P.recs[rec]);
+    q[0] = make_uint4(r.frame, r.flags, r.content_off, r.content_len);
+    q[1] = make_uint4(r.tc_first, (uint32_t)r.tc_count | ((uint32_t)r.n_choices << 16), r.usage, r.payload_len);
+    FLine &ln = S.line[line];
+    if (sf & SF_DONELINE) ln.flags |= LF_DONE;
+    if (terminates) atomicMin(&S.seg[ln.seg].term, line);
+}
+
+__device__ __noinline__ void t_build(const KParams &P, FSmem &S, uint32_t rslot, uint32_t ps, uint32_t pe, uint32_t rec_static,
+                                     uint32_t tflags, uint32_t n_choices, uint32_t tc_count, uint32_t tc_first);
+
 // A line retires: final syntax check, record, termination bookkeeping (agent.go:205-242).
 __device__ __forceinline__ void f_finish_line(const KParams &P, FSmem &S, FLane &L) {
     if (!(L.sf & SF_SYN)) {
@@ -707,90 +1036,237 @@ __device__ __forceinline__ void f_finish_line(const KParams &P, FSmem &S, FLane 
     }
     // a syntax error stops the walk: the rest of the payload has not been looked at for "[DONE]" (agent.go:181)
     if ((L.sf & SF_SYN) && (L.sf & SF_RMODE) && !(L.sf & SF_DONELINE) && has_done_scan(S, L.pe - L.plen, L.pe)) L.sf |= SF_DONELINE;
-    sse_rec r;
-    r.frame = SSE_NONE; r.flags = 0; r.content_off = r.content_len = 0; r.tc_first = SSE_NONE; r.tc_count = 0; r.n_choices = 0;
-    r.usage = SSE_NONE;
-    if (L.sf & SF_DEPTH) r.flags |= SSE_F_DEPTH_LIMIT;
-    if (L.sf & SF_DONELINE) r.flags |= SSE_F_DONE_LINE;      // swallowed by the reframe, parsed for agent.go:377-402
-    bool terminates = false;
-    if (!(L.sf & (SF_SYN | SF_TYPE))) {
-        r.flags |= SSE_F_JSON_OK;
-        r.n_choices = (uint16_t)min(L.n_choices, 0xFFFFu);
-        if ((L.sf & SF_USAGE) && L.usage_idx != SSE_NONE) { r.usage = L.usage_idx; r.flags |= SSE_F_HAS_USAGE; }
-        if (L.n_choices > 0) {
-            const Span ct = f_capture(P, S, L, L.content_pos, L.content_len, ((L.sf & SF_CDEC) ? 1u : 0u) | ((L.sf & SF_CBAD) ? 2u : 0u),
-                                      &P.recs[L.rec].content_len);
-            r.content_off = ct.len ? ct.off : 0; r.content_len = ct.len;
-            if (ct.text && ct.len) r.flags |= SSE_F_CONTENT_TEXT;
-            r.flags |= L.finish << SSE_F_FINISH_SHIFT;
-            if (L.sf & SF_TCNONNIL) r.flags |= SSE_F_TC_NONNIL;
-            if (L.sf & SF_TCVALID) r.flags |= SSE_F_TC_VALID;
-            r.tc_first = L.tc_count ? L.tc_first : SSE_NONE;
-            r.tc_count = (uint16_t)min(L.tc_count, 0xFFFFu);
-            if ((L.sf & SF_RMODE) && !(L.sf & SF_DONELINE) && (L.finish == SSE_FIN_STOP || L.finish == SSE_FIN_TOOL_CALLS)) {
-                r.flags |= SSE_F_TERMINATES;
-                terminates = true;
+    f_emit_record(P, S, L.sf, L.n_choices, L.usage_idx, L.content_pos, L.content_len, L.finish, L.tc_count, L.tc_first, L.rec, L.plen,
+                  L.line, L.delta);
+    L.busy = false;
+    if (L.rslot != SSE_NONE) {      // the automaton recorded this line: keep its skeleton as a template
+        const FRec &R = S.rec[L.rslot];
+        // one lane builds at a time (a second one, most likely holding the same skeleton, just drops its recording)
+        if (!R.nonsimple && !(L.sf & (SF_SYN | SF_TYPE | SF_DEPTH | SF_DONELINE)) && atomicCAS(&S.build_lock, 0u, 1u) == 0u) {
+            const uint32_t key = 2u * R.n_str + R.n_arr;
+            bool dup = false;        // another lane may have stored the same skeleton meanwhile
+            if (key < 255u)
+                for (uint32_t off = S.thead[key]; off && !dup; off = S.tstore[off] & 0xFFFFu) {
+                    uint32_t dummy = 0;
+                    dup = t_walk<false, false>(P, S, L, S.tstore + off, L.pe - L.plen, L.pe, SSE_NONE, dummy);
+                }
+            if (!dup) t_build(P, S, L.rslot, L.pe - L.plen, L.pe, SSE_F_JSON_OK | ((L.sf & SF_TCNONNIL) ? SSE_F_TC_NONNIL : 0u),
+                              ((L.sf & SF_USAGE) && L.usage_idx != SSE_NONE) ? TF_HAS_USAGE : 0u, L.n_choices, L.tc_count, L.tc_first);
+            __threadfence_block();
+            atomicExch(&S.build_lock, 0u);
+        }
+        atomicAnd(&S.rec_busy, ~(1u << L.rslot));
+        L.rslot = SSE_NONE;
+    }
+}
+
+// run template T's capture ops for the lane's line (its skeleton has just compared equal) and retire the line
+__device__ __forceinline__ void t_apply(const KParams &P, FSmem &S, FLane &L, const uint32_t *T, bool act) {
+    if (!act) { uint32_t d = 0; t_walk<true, true>(P, S, L, T, 0, 0, SSE_NONE, d, false); return; }
+    const uint32_t n_items = T[3] >> 16, tc_count = T[1] >> 24, tflags = (T[1] >> 16) & 0xFFu;
+    const uint32_t *tc_static = T + T_HDR + n_items;
+    uint32_t tc_base = SSE_NONE, tc_dyn = 0;
+    if (tflags & TF_HAS_USAGE) { L.usage_idx = f_usage_alloc(P); L.sf |= SF_USAGE; }
+    if (tc_count) tc_base = f_tcs_alloc(P, tc_count, tc_static);
+    L.finish = SSE_FIN_NONE; L.content_pos = L.content_len = 0;
+    t_walk<true, true>(P, S, L, T, L.p, L.pe, tc_base, tc_dyn, true);
+    L.n_choices = T[3] & 0xFFFFu;
+    if (T[2] & SSE_F_TC_NONNIL) L.sf |= SF_TCNONNIL;
+    L.tc_count = tc_base != SSE_NONE ? tc_count : 0u; L.tc_first = tc_base;
+    const uint8_t *st8 = reinterpret_cast<const uint8_t *>(tc_static);
+    for (uint32_t j = 0; j < tc_count; j++)
+        if ((st8[j] & SSE_TC_HAS_ID) || ((st8[j] & SSE_TC_HAS_FUNC) && ((tc_dyn >> (2u * j)) & 3u))) L.sf |= SF_TCVALID;
+    L.st = S_END; L.depth = 0; L.p = L.pe;
+    f_finish_line(P, S, L);
+}
+// Walk the chains: every lane of the warp tries its next candidate in the same iteration (the loop condition is
+// warp-uniform), so lanes that need more attempts do not fall out of step with the others. off: first candidate per lane
+// (0: none). Returns the template that fits (0: none).
+__device__ __forceinline__ uint32_t t_find(const KParams &P, FSmem &S, FLane &L, uint32_t off, uint32_t &vflags) {
+    uint32_t found = 0;
+    const uint32_t tail = L.plen >= 4u ? load4(S, L.pe - 4u) : 0u;
+    while (__any_sync(FULL, off != 0u)) {
+        // candidates whose last skeleton bytes differ from the line's are passed over right here
+        while (off && (L.plen < 4u || ((tail ^ S.tstore[off + 4u]) & S.tstore[off + 5u]))) off = S.tstore[off] & 0xFFFFu;
+        const uint32_t *T = S.tstore + off;
+        uint32_t vf = 0;
+        if (off) PCOUNT(48, 1);
+        const bool fit = t_walk<false, true>(P, S, L, T, L.p, L.pe, SSE_NONE, vf, off != 0u);
+        if (off) {
+            if (fit) { PCOUNT(49, 1); found = off; off = 0; vflags = vf; }
+            else off = T[0] & 0xFFFFu;
+        }
+    }
+    return found;
+}
+
+// The automaton has just retired a line it recorded (slot rslot): turn the recording into a template.
+__device__ __noinline__ void t_build(const KParams &P, FSmem &S, uint32_t rslot, uint32_t ps, uint32_t pe, uint32_t rec_static,
+                                     uint32_t tflags, uint32_t n_choices, uint32_t tc_count, uint32_t tc_first) {
+    const FRec &R = S.rec[rslot];
+    const uint32_t key = 2u * R.n_str + R.n_arr;
+    if (key >= 255u || tc_count > 15u) return;
+    const uint32_t n_items = (uint32_t)R.n + 1u;
+    uint32_t prev = ps, litw = 0, litb = 0;
+    for (uint32_t i = 0; i < R.n; i++) {
+        const uint32_t s = R.ev[i].start, e = s + R.ev[i].len;
+        if (s < prev || e > pe) return;
+        litw += (s - prev + 3u) >> 2; litb += s - prev; prev = e;
+    }
+    litw += (pe - prev + 3u) >> 2; litb += pe - prev;
+    if (litb > T_LIT_MAX) return;
+    const uint32_t words = T_HDR + n_items + (tc_count ? 4u : 0u) + litw;
+    const uint32_t off = atomicAdd(&S.ts_used, words);
+    if (off + words > (uint32_t)TS_WORDS) { atomicSub(&S.ts_used, words); return; }
+    uint32_t *T = S.tstore + off;
+    {
+        const uint32_t endlit = pe - prev;                       // skeleton bytes behind the last wildcard: a cheap first test
+        const uint32_t tn = min(endlit, 4u);
+        const uint32_t tmask = tn == 4u ? 0xFFFFFFFFu : tn == 0u ? 0u : ~((1u << ((4u - tn) * 8u)) - 1u);     // the high tn bytes of load4(pe - 4)
+        T[4] = pe - ps >= 4u ? (load4(S, pe - 4u) & tmask) : 0u; T[5] = pe - ps >= 4u ? tmask : 0u;
+        bool simple = !(tflags & TF_HAS_USAGE) && tc_count == 0;
+        for (uint32_t i = 0; i < R.n; i++) { const uint32_t c = R.ev[i].op & 15u; if (c != OP_NONE && c != OP_CONTENT && c != OP_FINISH && c != OP_CHK_I64 && c != OP_CHK_F32) simple = false; }
+        if (simple) tflags |= TF_SIMPLE;
+    }
+    T[0] = key << 16; T[1] = litb | (tflags << 16) | (tc_count << 24); T[2] = rec_static; T[3] = n_choices | (n_items << 16);
+    uint32_t *items = T + T_HDR, *tcs = items + n_items, *lw = tcs + (tc_count ? 4u : 0u);
+    if (tc_count) {
+        uint32_t w4[4] = { 0, 0, 0, 0 }, t = tc_first;
+        for (uint32_t j = 0; j < tc_count && t != SSE_NONE; j++) { w4[j >> 2] |= (P.tcs[t].flags & 7u) << ((j & 3u) * 8u); t = P.tcs[t].next; }
+        tcs[0] = w4[0]; tcs[1] = w4[1]; tcs[2] = w4[2]; tcs[3] = w4[3];
+    }
+    prev = ps;
+    for (uint32_t i = 0; i < n_items; i++) {
+        const bool last = i + 1u == n_items;
+        const uint32_t s = last ? pe : (uint32_t)R.ev[i].start;
+        const uint32_t lit = s - prev;
+        items[i] = lit | ((last ? (uint32_t)WK_END : (uint32_t)R.ev[i].kind) << 16) | ((last ? 0u : (uint32_t)R.ev[i].op) << 24);
+        for (uint32_t j = 0; j < lit; j += 4u) {
+            uint32_t v = load4(S, prev + j);
+            if (lit - j < 4u) v &= (1u << ((lit - j) * 8u)) - 1u;
+            *lw++ = v;
+        }
+        prev = last ? pe : s + R.ev[i].len;
+    }
+    PCOUNT(51, 1); PCOUNT(52, words);
+    __threadfence_block();
+    const uint32_t old = atomicExch(&S.thead[key], off);      // published: readers see a complete template
+    T[0] = (key << 16) | (old & 0xFFFFu);
+}
+
+// lane state for the line of decode job j (everything both paths need)
+__device__ __forceinline__ uint32_t lane_setup(const KParams &P, const FSmem &S, FLane &L, uint32_t j, uint32_t rb) {
+    const uint32_t k = S.job[j];
+    const FLine ln = S.line[k];
+    const FSeg &sg = S.seg[ln.seg];
+    const uint32_t pay_s = (ln.flags & LF_PREF) ? ln.a + 6u : ln.a;
+    L.p = pay_s; L.pe = ln.b; L.plen = L.pe - L.p; L.line = k;
+    L.rec = rb + ln.rank_r;
+    const uint32_t src_s = (ln.flags & LF_RMODE) ? ln.a : ln.start;
+    L.delta = (ln.flags & LF_ZC) ? P.in_base + sg.in_delta : ln.out_off - src_s;
+    L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.slen = 0;
+    L.sf = ((ln.flags & LF_RMODE) ? SF_RMODE : 0u) | ((ln.flags & LF_DONE) ? SF_DONELINE : 0u);
+    L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
+    L.content_pos = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = L.tc_cur = SSE_NONE; L.tcb = 0;
+    L.usage_idx = SSE_NONE; L.rslot = SSE_NONE;
+    L.busy = true;
+    return ln.pad;
+}
+
+// Template path of stage 2 for one pass of jobs (own function: its registers are not the automaton's). Every lane of the
+// warp calls it; has: the lane holds job j. Returns true when the lane's line was retired through a template.
+__device__ __noinline__ bool stage2_replay(const KParams &P, FSmem &S, bool has, uint32_t j, uint32_t rb) {
+    FLane L;
+    L.busy = false; L.p = L.pe = 0; L.plen = 0; L.sf = 0; L.rslot = SSE_NONE; L.line = 0; L.rec = 0; L.delta = 0;
+    L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.slen = 0; L.choices_count = L.n_choices = 0; L.finish = 0;
+    L.ct = L.ct1 = L.sstk = 0; L.content_pos = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = L.tc_cur = SSE_NONE;
+    L.tcb = 0; L.usage_idx = SSE_NONE;
+#ifdef SSE_PROF
+    long long ts_ = clock64();
+#endif
+    uint32_t key = 255u;
+    if (has) key = lane_setup(P, S, L, j, rb);
+    // swallowed "[DONE]" lines go to the automaton: their flag is not part of a template
+    const bool cand = has && !(L.sf & SF_DONELINE);
+    PSTAMP(0);
+    uint32_t vflags = 0, toff = 0;
+    uint32_t first = (cand && key < 255u) ? S.thead[key] : 0u;
+    #pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const uint32_t f = t_find(P, S, L, first, vflags);
+        if (f) toff = f;
+        // escapes and non-ASCII bytes in string values add stop bytes: look under the clean count too
+        const bool miss = cand && !toff && pass == 0;
+        if (!__any_sync(FULL, miss)) break;
+        const uint32_t key2 = miss ? t_clean_key(S, L.p, L.pe) : 255u;
+        first = (miss && key2 < 255u && key2 != key) ? S.thead[key2] : 0u;
+        PSTAMP(1);
+    }
+    PSTAMP(2);
+    {   // the record is written, the lane retires
+        const uint32_t *T = S.tstore + toff;
+        const bool simple = toff && ((T[1] >> 16) & TF_SIMPLE) && !(vflags & 0x80000000u);
+        if (simple) {                                    // everything was captured while comparing
+            if (vflags & 0x40000000u) L.sf |= SF_DONELINE;
+            L.n_choices = T[3] & 0xFFFFu;
+            if (T[2] & SSE_F_TC_NONNIL) L.sf |= SF_TCNONNIL;
+            L.st = S_END; L.depth = 0; L.p = L.pe;
+            f_finish_line(P, S, L);
+        }
+        const bool full = toff && !simple;               // usage / tool-call / range-check ops: a second walk
+        if (__any_sync(FULL, full)) t_apply(P, S, L, T, full);
+    }
+    PSTAMP(3);
+    if (cand && !toff) PCOUNT(50, 1);
+    return toff != 0;
+}
+
+// Automaton path of stage 2: the lanes whose line no template took.
+__device__ __noinline__ void stage2_automaton(const KParams &P, FSmem &S, bool has, uint32_t j, uint32_t rb) {
+    FLane L;
+    L.busy = false; L.p = L.pe = 0; L.plen = 0; L.sf = 0; L.rslot = SSE_NONE; L.line = 0; L.rec = 0; L.delta = 0;
+    L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.slen = 0; L.choices_count = L.n_choices = 0; L.finish = 0;
+    L.ct = L.ct1 = L.sstk = 0; L.content_pos = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = L.tc_cur = SSE_NONE;
+    L.tcb = 0; L.usage_idx = SSE_NONE;
+    if (has) {
+        lane_setup(P, S, L, j, rb);
+        if (!(P.flags & SSE_FLAG_NO_TEMPLATES) && !(L.sf & SF_DONELINE) && S.ts_used + 128u < (uint32_t)TS_WORDS) {
+            uint32_t m = S.rec_busy;                 // record a template while the automaton walks the line
+            while ((~m) & ((1u << NREC) - 1u)) {
+                const uint32_t b = (uint32_t)__ffs((~m) & ((1u << NREC) - 1u)) - 1u;
+                const uint32_t old = atomicCAS(&S.rec_busy, m, m | (1u << b));
+                if (old == m) { PCOUNT(53, 1); L.rslot = b; FRec &R = S.rec[b]; R.n = 0; R.nonsimple = 0; R.n_str = 0; R.n_arr = 0; break; }
+                m = old;
             }
         }
     }
-    r.payload_len = L.plen;
-    uint4 *q = reinterpret_cast<uint4 *>(&P.recs[L.rec]);
-    q[0] = make_uint4(r.frame, r.flags, r.content_off, r.content_len);
-    q[1] = make_uint4(r.tc_first, (uint32_t)r.tc_count | ((uint32_t)r.n_choices << 16), r.usage, r.payload_len);
-    FLine &ln = S.line[L.line];
-    if (L.sf & SF_DONELINE) ln.flags |= LF_DONE;
-    if (terminates) atomicMin(&S.seg[ln.seg].term, L.line);
-    L.busy = false;
+    while (__any_sync(FULL, L.busy)) {
+        #pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+            f_step(P, S, L);
+            if (L.busy && L.p >= L.pe) f_finish_line(P, S, L);
+        }
+    }
 }
 
 __device__ void stage2(const KParams &P, FSmem &S, uint32_t n_jobs, uint32_t rb) {
-    const uint32_t lane = threadIdx.x & 31u;
-    // jobs are ordered by shape (stage 1b): the 32 lines of a warp are alike and walk in lockstep
-    FLane L;
-    L.busy = false; L.p = L.pe = 0; L.jpatch = nullptr; L.js = L.je = L.jdst = 0;
-    L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
-    L.finish = 0; L.ct = L.ct1 = L.sstk = 0; L.content_pos = L.content_len = 0; L.tc_count = 0;
-    L.tc_first = L.tc_prev = L.tc_cur = SSE_NONE; L.tcb = 0; L.usage_idx = SSE_NONE; L.rec = L.delta = L.plen = L.line = 0;
-    // every warp takes an equal share of consecutive jobs: fewer lanes per warp, but all warps of the CTA walk lines
-    const uint32_t wid = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     for (uint32_t base = 0; base < n_jobs; base += F_THREADS) {
         const uint32_t left = min(n_jobs - base, (uint32_t)F_THREADS);
-        const uint32_t lpw = (left + F_WARPS - 1u) / F_WARPS;           // lanes per warp in this pass
-        const uint32_t j = base + wid * lpw + lane;
-        if (lane < lpw && j < n_jobs) {
-            const uint32_t k = S.job[j];
-            const FLine ln = S.line[k];
-            const FSeg &sg = S.seg[ln.seg];
-            const uint32_t pay_s = (ln.flags & LF_PREF) ? ln.a + 6u : ln.a;
-            L.p = pay_s; L.pe = ln.b; L.plen = L.pe - L.p; L.line = k;
-            L.rec = rb + ln.rank_r;
-            const uint32_t src_s = (ln.flags & LF_RMODE) ? ln.a : ln.start;
-            L.delta = (ln.flags & LF_ZC) ? P.in_base + sg.in_delta : ln.out_off - src_s;
-            L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.slen = 0;
-            L.sf = ((ln.flags & LF_RMODE) ? SF_RMODE : 0u) | ((ln.flags & LF_DONE) ? SF_DONELINE : 0u);
-            L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
-            L.content_pos = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = L.tc_cur = SSE_NONE; L.tcb = 0;
-            L.usage_idx = SSE_NONE;
-            L.busy = true;
+#ifndef SSE_LPW
+#define SSE_LPW 32
+#endif
+        // SSE_LPW consecutive jobs (lines of the same streams: the same templates) per warp
+        const uint32_t lpw = max(min((uint32_t)SSE_LPW, 32u), (left + F_WARPS - 1u) / F_WARPS);
+        if (wid * lpw >= left) break;                        // no line for this warp (warp-uniform)
+        const uint32_t j = lane < lpw ? base + wid * lpw + lane : n_jobs;
+        const bool has = j < n_jobs;
+        bool todo = has;
+        if (!(P.flags & SSE_FLAG_NO_TEMPLATES)) {
+            const bool hit = stage2_replay(P, S, has, j, rb);      // (every lane makes the call: it holds warp-wide votes)
+            todo = has && !hit;
         }
-        while (__any_sync(FULL, L.busy)) {
-            #pragma unroll 1
-            for (int r = 0; r < 4; r++) {
-                f_step(P, S, L);
-                if (L.busy && L.p >= L.pe) f_finish_line(P, S, L);
-            }
-            // strings that need unquoting: decoded by the whole warp
-            __syncwarp();
-            unsigned jm = __ballot_sync(FULL, L.jpatch != nullptr);
-            while (jm) {
-                const int leader = __ffs(jm) - 1;
-                jm &= jm - 1;
-                const uint32_t js = __shfl_sync(FULL, L.js, leader), je = __shfl_sync(FULL, L.je, leader), jd = __shfl_sync(FULL, L.jdst, leader);
-                const unsigned long long pp = __shfl_sync(FULL, (unsigned long long)(uintptr_t)L.jpatch, leader);
-                warp_unquote(S.tile, js, je, P.text + jd, reinterpret_cast<uint32_t *>((uintptr_t)pp));
-                if ((int)lane == leader) L.jpatch = nullptr;
-            }
-        }
+        if (__any_sync(FULL, todo)) stage2_automaton(P, S, todo, j, rb);
     }
 }
 
@@ -837,7 +1313,7 @@ __device__ void process_window(const KParams &P, FSmem &S, uint32_t first_seg, u
         }
         const uint32_t n_lines = min(total, (uint32_t)LCAP);
         if (tid < nseg) { FSeg &sg = S.seg[tid]; sg.term = SSE_NONE; sg.dead = SSE_NONE; sg.rf0 = SSE_NONE; sg.rr0 = SSE_NONE; sg.fcnt = 0; sg.rcnt = 0; }
-        if (tid == 0) S.bc[9] = 0;               // materialised lines of this round
+        if (tid == 0) { S.bc[9] = 0; S.jq_n = 0; }    // materialised lines, unquote jobs of this round
         __syncthreads();
         if (n_lines == 0) break;
 
@@ -897,33 +1373,16 @@ __device__ void process_window(const KParams &P, FSmem &S, uint32_t first_seg, u
         __syncthreads();
         const uint32_t rb = S.bc[1], ob = S.bc[2];
         if (S.bc[3]) return;                      // the batch is reported as overflowed: stop touching result arenas
-        // decode jobs ordered by shape key (counting sort): the lanes of a warp then walk lines of the same JSON shape
-        uint32_t key = 0, krank = 0;
-        if (tid < N_SHAPES) S.hist[tid] = 0;
-        __syncthreads();
+        // template bucket of a line to decode: its number of stop bytes (stage 2)
         if (k < n_lines && (lflags & LF_JOB)) {
             const FLine &ln = S.line[k];
-            key = min(count_stops(S, (lflags & LF_PREF) ? ln.a + 6u : ln.a, ln.b), (uint32_t)N_SHAPES - 1u);
-            krank = atomicAdd(&S.hist[key], 1u);
+            S.line[k].pad = (uint8_t)min(count_stops(S, (lflags & LF_PREF) ? ln.a + 6u : ln.a, ln.b), 255u);
         }
-        __syncthreads();
-        if (w == 0) {
-            uint32_t h[N_SHAPES / 32], sum = 0;
-            #pragma unroll
-            for (int i = 0; i < N_SHAPES / 32; i++) { h[i] = S.hist[lane * (N_SHAPES / 32) + i]; sum += h[i]; }
-            uint32_t incl = sum;
-            #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(FULL, incl, d); if ((int)lane >= d) incl += x; }
-            uint32_t run = incl - sum;
-            #pragma unroll
-            for (int i = 0; i < N_SHAPES / 32; i++) { S.hist[lane * (N_SHAPES / 32) + i] = run; run += h[i]; }
-        }
-        __syncthreads();
         if (k < n_lines) {
             FLine &ln = S.line[k];
             ln.flags = (uint16_t)(kind | lflags | (mat ? LF_MAT : 0));
             ln.rank_r = (uint16_t)vr; ln.out_off = ob + vb;
-            if (lflags & LF_JOB) S.job[S.hist[key] + krank] = (uint16_t)k;
+            if (lflags & LF_JOB) S.job[vrj >> 16] = (uint16_t)k;
             if (kind == K_DONE_EXACT) {
                 sse_rec r; r.frame = SSE_NONE; r.flags = SSE_F_DONE_LINE | SSE_F_DONE_EXACT; r.content_off = r.content_len = 0;
                 r.tc_first = SSE_NONE; r.tc_count = 0; r.n_choices = 0; r.usage = SSE_NONE; r.payload_len = 6;
@@ -937,6 +1396,10 @@ __device__ void process_window(const KParams &P, FSmem &S, uint32_t first_seg, u
         PROF(8);
         __syncthreads();
         PROF(4);
+        for (uint32_t i = w; i < min(S.jq_n, (uint32_t)JQ_CAP); i += F_WARPS) {      // unquote jobs: one warp per string
+            const FJob jb = S.jq[i];
+            if (jb.patch) warp_unquote2(S.tile, jb.s, jb.e, P.text + jb.dst, jb.patch);
+        }
         // ---------------- frames (after early termination is known), record -> frame links, runs
         uint32_t vf = 0, tot_f;
         bool in_cut = false;
@@ -1083,7 +1546,19 @@ sse_fused_kernel(const __grid_constant__ KParams P, const FTables *__restrict__ 
         uint32_t *dst = reinterpret_cast<uint32_t *>(&S.T);
         for (int i = tid; i < (int)(sizeof(FTables) / 4); i += F_THREADS) dst[i] = src[i];
     }
-    if (tid == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); S.rec_busy = 0; S.build_lock = 0; }
+    if (tid < 256) S.thead[tid] = 0;
+    // the templates learnt by earlier launches (a cache: results never depend on what it holds)
+    uint32_t t_loaded = 1;
+    if (P.tcache) {
+        t_loaded = min(max(P.tcache[0], 1u), (uint32_t)TS_WORDS);
+        if (t_loaded > 1u) {
+            for (uint32_t i = tid; i < 256u; i += F_THREADS) S.thead[i] = P.tcache[1u + i];
+            for (uint32_t i = tid; i < t_loaded; i += F_THREADS) S.tstore[i] = P.tcache[257u + i];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) S.ts_used = t_loaded;
     __syncthreads();
     uint32_t phase = 0;
     const uint32_t n_tiles = min(P.ctr->n_tiles, P.cap_tiles);
@@ -1091,11 +1566,23 @@ sse_fused_kernel(const __grid_constant__ KParams P, const FTables *__restrict__ 
     if (tid == 0) S.prof_t = clock64();
 #endif
 
+    if (tid == 0) S.bc[0] = atomicAdd(&P.ctr->ticket, 1u);
+    __syncthreads();
+    uint32_t t_next = S.bc[0];
     for (;;) {
-        if (tid == 0) S.bc[0] = atomicAdd(&P.ctr->ticket, 1u);
-        __syncthreads();
-        const uint32_t t = S.bc[0];
+        const uint32_t t = t_next;
         if (t >= n_tiles) break;
+        __syncthreads();
+        if (tid == 0) S.bc[0] = atomicAdd(&P.ctr->ticket, 1u);       // tickets are taken one tile ahead ...
+        __syncthreads();
+        t_next = S.bc[0];
+        if (t_next < n_tiles) {                                         // ... so that the next tile's bytes are on their way to L2
+            const uint2 tn = P.tiles[t_next];
+            if (tid < tn.y) {
+                const sse_seg nx = P.segs[tn.x + tid];
+                if (nx.in_len) bulk_prefetch_l2(P.in + nx.in_off, (nx.in_len + 15u) & ~15u);
+            }
+        }
         const uint2 td = P.tiles[t];
         const uint32_t first = td.x, nseg = td.y;
 
@@ -1200,6 +1687,18 @@ sse_fused_kernel(const __grid_constant__ KParams P, const FTables *__restrict__ 
             }
             if (w == 0) finish_segment(P, S, first, 0);
             __syncthreads();
+        }
+    }
+    // one CTA hands what it has learnt to the next launch (all CTAs see the same kinds of lines)
+    if (P.tcache && blockIdx.x == 0) {
+        __syncthreads();
+        const uint32_t used = min(S.ts_used, (uint32_t)TS_WORDS);
+        if (used > t_loaded) {
+            for (uint32_t i = tid; i < used; i += F_THREADS) P.tcache[257u + i] = S.tstore[i];
+            for (uint32_t i = tid; i < 256u; i += F_THREADS) P.tcache[1u + i] = S.thead[i];
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) P.tcache[0] = used;
         }
     }
 }
@@ -1316,7 +1815,7 @@ int sse_fused_prepare(int device) {
 
 extern "C" int sse_prof_read(unsigned long long *out16) {
 #ifdef SSE_PROF
-    unsigned long long z[16] = { 0 };
+    unsigned long long z[160] = { 0 };
     if (cudaMemcpyFromSymbol(out16, g_prof, sizeof z) != cudaSuccess) return -1;
     cudaMemcpyToSymbol(g_prof, z, sizeof z);
     return 0;
@@ -1326,6 +1825,7 @@ extern "C" int sse_prof_read(unsigned long long *out16) {
 }
 
 uint32_t sse_fused_max_line(void) { return TILE - 32u; }
+uint32_t sse_fused_tcache_words(void) { return 257u + TS_WORDS; }
 
 int sse_launch_fused(const KParams &p, void *stream, int sm_count, int device) {
     const uint32_t groups = (p.n_segs + PLAN_GROUP - 1) / PLAN_GROUP;

@@ -60,6 +60,7 @@ struct sse_ctx {
     sse_config cfg{};
     ConnState *d_conns = nullptr;
     uint8_t *d_carry = nullptr;
+    uint32_t *d_tcache = nullptr;        // fused kernel: skeleton templates kept between launches
     cudaStream_t ctl_stream = nullptr;
     cudaEvent_t last_kernel = nullptr;   // completion of the most recently launched kernel
     bool have_last = false;
@@ -98,6 +99,7 @@ KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
     p.items = s.d_items; p.cap_items = c->cfg.max_recs; p.seg_term = s.d_segterm;
     p.items_sorted = s.d_items2; p.flags = c->cfg.flags;
     p.tiles = s.d_tiles; p.cap_tiles = c->cfg.max_segs + 64;
+    p.tcache = (c->cfg.flags & SSE_FLAG_NO_TEMPLATES) ? nullptr : c->d_tcache;
     return p;
 }
 
@@ -215,7 +217,7 @@ void sse_worst_case_config(sse_config *cfg, uint32_t max_conns, uint32_t bytes_p
     sse_default_config(cfg, max_conns, bytes_per_batch);
     const uint64_t in = cfg->in_arena_bytes, cap = 0xF0000000ull;
     auto clamp = [&](uint64_t v) { return (uint32_t)(v > cap ? cap : v); };
-    cfg->carry_slot_bytes = 65504;                                   // longest line the fused kernel supports
+    cfg->carry_slot_bytes = sse_fused_max_line() & ~15u;             // longest line the fused kernel supports
     cfg->max_frames = clamp(in + 64);                                // a frame needs its own '\n' in this batch
     cfg->max_recs = clamp(in / 4 + 2ull * max_conns + 64);           // "data: x\n" is 8 bytes; one carried line per segment
     cfg->max_usages = cfg->max_recs;
@@ -256,6 +258,8 @@ int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
     ok = ok && dalloc(c->d_conns, cfg->max_conns);
     ok = ok && dalloc(c->d_carry, (size_t)cfg->max_conns * cfg->carry_slot_bytes);
     ok = ok && cu_ok(cudaMemset(c->d_conns, 0, (size_t)cfg->max_conns * sizeof(ConnState)), "cudaMemset");
+    ok = ok && dalloc(c->d_tcache, sse_fused_tcache_words());
+    ok = ok && cu_ok(cudaMemset(c->d_tcache, 0, (size_t)sse_fused_tcache_words() * sizeof(uint32_t)), "cudaMemset");
     c->slots.resize(cfg->n_slots);
     for (auto &s : c->slots) {
         if (!ok) break;
@@ -285,7 +289,7 @@ void sse_destroy(sse_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &s : c->slots) free_slot(s);
-    cudaFree(c->d_conns); cudaFree(c->d_carry);
+    cudaFree(c->d_conns); cudaFree(c->d_carry); cudaFree(c->d_tcache);
     if (c->ctl_stream) cudaStreamDestroy(c->ctl_stream);
     if (c->last_kernel) cudaEventDestroy(c->last_kernel);
     delete c;
@@ -386,6 +390,16 @@ int sse_download(sse_ctx *c, int slot, sse_result *res, void *cuda_stream) {
     if (s.state != SLOT_ACQUIRED) return SSE_ERR_BUSY;
     CU(cudaSetDevice(c->device));
     return do_download(c, s, res, cuda_stream ? (cudaStream_t)cuda_stream : s.stream);
+}
+
+/* debugging aid (tools/dump_templates.py): the fused kernel's template cache, as sse_fused.cu lays it out */
+int sse_debug_tcache(sse_ctx *c, uint32_t *out, uint32_t words) {
+    if (!c || !out || !c->d_tcache) return SSE_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    const uint32_t n = words < sse_fused_tcache_words() ? words : sse_fused_tcache_words();
+    CU(cudaMemcpy(out, c->d_tcache, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return (int)n;
 }
 
 int sse_launch_count(sse_ctx *c, uint64_t *kernel_launches) {

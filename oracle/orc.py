@@ -89,7 +89,7 @@ def lib():
         _lib.orc_telemetry.restype = C.c_size_t
         _lib.orc_last_builder.argtypes = [C.POINTER(Result), C.POINTER(C.c_size_t)]
         _lib.orc_last_builder.restype = C.POINTER(C.c_uint8)
-        _lib.orc_bench_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+        _lib.orc_bench_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _lib.orc_bench_run.restype = C.c_double
     return _lib
@@ -245,11 +245,12 @@ def telemetry(body: bytes, cap: int = 256):
         L.orc_result_free(rp)
 
 
-def bench_run(arena, off, length, mode, n_threads: int):
+def bench_run(arena, off, length, mode, n_threads: int, passes: int = 1):
     """arena: np.uint8 array; off: np.uint64; length: np.uint32; mode: np.uint8 (bit0 R, bit1 parse).
-    Returns (seconds, out_bytes, frames, chunks_ok)."""
+    One pool of n_threads threads runs `passes` passes over the streams. Returns (seconds, out_bytes, frames, chunks_ok),
+    totals over all passes."""
     L = lib()
     ob, fr, ok = C.c_uint64(), C.c_uint64(), C.c_uint64()
     secs = L.orc_bench_run(arena.ctypes.data, off.ctypes.data, length.ctypes.data, mode.ctypes.data,
-                           len(off), n_threads, C.byref(ob), C.byref(fr), C.byref(ok))
+                           len(off), n_threads, passes, C.byref(ob), C.byref(fr), C.byref(ok))
     return secs, ob.value, fr.value, ok.value

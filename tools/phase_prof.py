@@ -12,7 +12,7 @@ eng = SseEngine(device=0, max_conns=n, bytes_per_batch=tot, n_slots=1, carry_slo
 slot, arena, segs = eng.acquire()
 ns, nb = eng.fill(arena, segs, [(i, A.MODE_R | A.MODE_PARSE, b) for i, b in enumerate(bodies)])
 eng.upload(slot, ns, nb)
-out = (C.c_ulonglong * 16)()
+out = (C.c_ulonglong * 160)()
 names = ["setup+load", "stage1a", "enum+classify", "alloc+sort", "barrier after stage2", "frames+serialize", "runs", "finish_segment", "stage2 (thread 0's warp)"]
 import torch
 for it in range(4):
@@ -23,3 +23,14 @@ s = sum(v[:8])
 print(f"{wl} {n} streams, {tot/1e6:.1f} MB")
 for i, nm in enumerate(names):
     print(f"{nm:28s} {v[i]/1e6:10.1f} Mcycles {v[i]/s*100 if i < 8 else v[i]/s*100:5.1f}%")
+
+print("per-warp stage 2: Mcycles / loop iterations (x4 steps) / cycles per iteration")
+for w_ in range(16):
+    c_, i_ = v[16 + w_], v[32 + w_]
+    print(f"  warp {w_:2d}: {c_/1e6:8.1f} Mcyc {i_/1e6:8.2f} Miter {c_/max(i_,1):8.1f} cyc/iter")
+
+print("templates: verify attempts %d, hits %d, automaton lines %d, templates built %d (%d words), recordings %d" % tuple(v[48:54]))
+
+print("stage 2 sub-phases per warp (Mcycles): setup / find(raw key) / clean key + find / apply")
+for w_ in range(16):
+    print("  warp %2d: " % w_ + " ".join("%8.1f" % (v[64 + k * 16 + w_] / 1e6) for k in range(4)))
