@@ -23,6 +23,7 @@
 // Pure integer/byte work, no tensor cores.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "sse_common.cuh"
 #include "sse_tables.h"
 
@@ -32,15 +33,18 @@ using namespace ssetab;
 
 constexpr int F_THREADS = 512;
 constexpr int F_WARPS = F_THREADS / 32;
-constexpr uint32_t TILE = 53248;
+constexpr uint32_t TILE = 49152;
 constexpr uint32_t TILE_PAD = 64;
 constexpr uint32_t BM_WORDS = TILE / 32;
-constexpr int MAX_TSEGS = 128;
+constexpr int MAX_TSEGS = 96;
 constexpr int LCAP = F_THREADS;            // lines per round: one thread per line
 constexpr int PLAN_GROUP = 1024;
-constexpr int TS_WORDS = 4096;             // template store (32-bit words)
-constexpr int NREC = 8, REC_MAX = 40;      // lanes recording a template at the same time; wildcards per template
-constexpr int JQ_CAP = 96;
+constexpr int TS_WORDS = 3328;             // template store (32-bit words)
+constexpr int NREC = 6, REC_MAX = 40;      // lanes recording a template at the same time; wildcards per template
+constexpr int JQ_CAP = 64;
+constexpr int W_STOPS = 96, W_STRUCT = 64;  // stop bytes / structural stops of a line the warp-per-line replay handles
+struct FWarp { uint16_t spos[W_STOPS]; uint16_t sstop[W_STRUCT + 2]; uint32_t sdirty[(W_STRUCT + 8) / 4]; };   // sdirty: one byte per segment
+struct FRes { uint16_t cpos, clen, toff, misc; };   // template captures of a line (misc: d2 | finish << 2 | done 32 | pending 64 | written 128)
 struct FJob { uint32_t s, e, dst, pad; uint32_t *patch; };
 struct FRecEv { uint16_t start, len; uint8_t kind, op; };
 struct FRec { uint16_t n, nonsimple, n_str, n_arr; FRecEv ev[REC_MAX]; };           // segments packed into tiles by one warp of the plan kernel
@@ -89,10 +93,12 @@ struct FSmem {
     FSeg seg[MAX_TSEGS];
     FTables T;
     uint32_t tstore[TS_WORDS];             // skeleton templates of this CTA (kept for the whole launch)
-    uint32_t thead[256];                   // bucket (clean stop count) -> newest template
+    uint32_t thead[W_STRUCT + 8];          // bucket (number of structural stops) -> newest template
     FRec rec[NREC];
     uint32_t ts_used, rec_busy, build_lock;
     FJob jq[JQ_CAP];                       // strings of this round that need unquoting
+    FRes res[LCAP];                        // per decode job: what a template captured
+    FWarp wsc[F_WARPS];                    // warp scratch of the replay
     uint32_t jq_n;
     alignas(8) unsigned long long mbar;
     uint32_t scan_a[F_WARPS], scan_b[F_WARPS];
@@ -138,6 +144,16 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---------------------------------------------------------------- out-of-line copies of shared helpers
+// The steady-state path of this kernel has to fit the SM's 32 KB instruction cache (L1.5): everything that is big or rare
+// is kept out of line, once.
+__device__ __noinline__ void copy_s2g(uint8_t *__restrict__ g_dst, const uint8_t *__restrict__ sm_src, int n) { copy_s2g_vec(g_dst, sm_src, n); }
+__device__ __noinline__ uint32_t trim_space_ab(const uint8_t *s, uint32_t a, uint32_t b) {     // strings.TrimSpace: a | b << 16
+    int ia = (int)a, ib = (int)b;
+    trim_space(s, ia, ib);
+    return (uint32_t)ia | ((uint32_t)ib << 16);
+}
+
 // ---------------------------------------------------------------- block helpers
 // exclusive prefix sums over the block (thread order); the totals come back too. Two barriers each.
 __device__ __forceinline__ uint32_t warp_incl(uint32_t v, uint32_t lane) {
@@ -145,7 +161,7 @@ __device__ __forceinline__ uint32_t warp_incl(uint32_t v, uint32_t lane) {
     for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(FULL, v, d); if ((int)lane >= d) v += x; }
     return v;
 }
-__device__ __forceinline__ uint32_t block_scan1(FSmem &S, uint32_t a, uint32_t &ta) {
+__device__ __noinline__ uint32_t block_scan1(FSmem &S, uint32_t a, uint32_t &ta) {
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t ia = warp_incl(a, lane);
     if (lane == 31) S.scan_a[w] = ia;
@@ -156,7 +172,7 @@ __device__ __forceinline__ uint32_t block_scan1(FSmem &S, uint32_t a, uint32_t &
     __syncthreads();
     return (w ? ba : 0u) + ia - a;
 }
-__device__ __forceinline__ void block_scan2(FSmem &S, uint32_t &a, uint32_t &b, uint32_t &ta, uint32_t &tb) {
+__device__ __noinline__ void block_scan2(FSmem &S, uint32_t &a, uint32_t &b, uint32_t &ta, uint32_t &tb) {
     const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const uint32_t ia = warp_incl(a, lane), ib = warp_incl(b, lane);
     if (lane == 31) { S.scan_a[w] = ia; S.scan_b[w] = ib; }
@@ -211,6 +227,7 @@ __device__ __forceinline__ void stage1a(FSmem &S, uint32_t fill) {
 __device__ __forceinline__ uint32_t next_stop(const FSmem &S, uint32_t p, uint32_t pe) {
     uint32_t w = p >> 5;
     uint32_t bits = S.stopbm[w] & (0xFFFFFFFFu << (p & 31u));
+    #pragma unroll 1
     while (bits == 0) {
         w++;
         if ((w << 5) >= pe) return pe;
@@ -238,6 +255,7 @@ __device__ __forceinline__ uint32_t count_stops(const FSmem &S, uint32_t a, uint
     const uint32_t we = (b - 1u) >> 5;
     uint32_t bits = S.stopbm[w] & (0xFFFFFFFFu << (a & 31u));
     uint32_t n = 0;
+    #pragma unroll 1
     for (; w < we; w++) { n += __popc(bits); bits = S.stopbm[w + 1]; }
     const uint32_t r = b & 31u;
     if (r) bits &= (1u << r) - 1u;
@@ -808,146 +826,61 @@ after_value:
 }
 // ---------------------------------------------------------------- skeleton templates
 // Consecutive chunks of a stream -- and the chunks of every other stream of the same provider -- differ only inside string
-// values and integers: keys, punctuation, literals are byte for byte the same. A line parsed by the automaton above leaves a
-// template in the CTA's cache: its bytes outside those wildcards (the skeleton) and, per wildcard, what the parse did with
-// it (capture op). A later line whose skeleton compares equal, and whose wildcards are again a well-formed string body /
-// an integer, takes the automaton through exactly the same transitions -- so its record is the template's with its own
-// spans, and the automaton does not have to run. The compare-and-scan loop is the same code for every template: the lanes
-// of a warp stay together whatever mix of lines they hold. Lines that match no template take the automaton (and record one).
+// values and integers: keys, punctuation and literals are byte for byte the same. A line the automaton has parsed leaves a
+// template in the CTA's cache: its structural stops (the quotes that open and close strings, and '[' outside strings), and
+// for every segment between two of them either its bytes (keys, punctuation), "a string body", or "punctuation around an
+// integer", plus what the parse did with the captured ones. A later line whose structural stops and segments compare equal,
+// and whose string bodies / integers are well formed, takes the automaton through exactly the same transitions: its record
+// is the template's with its own spans. The comparison is done by a whole warp per line -- one lane per stop, then one lane
+// per segment, string parity and stop ranks by ballot -- so its cost does not depend on what the other lines look like.
+// Lines that fit no template go to the automaton (one lane per line), which records a template for them.
 constexpr uint32_t T_LIT_MAX = 1024;       // skeleton bytes per template
-constexpr uint32_t TF_HAS_USAGE = 1, TF_SIMPLE = 2;   // TF_SIMPLE: only content / finish_reason / range-check ops: no second walk
-constexpr uint32_t T_HDR = 6;                           // header words
-// template in the store: [0] next | key << 16   [1] skeleton bytes | flags << 16 | tc_count << 24   [2] static record flags
-// [3] n_choices | n_items << 16   [4] the last (up to 4) bytes of the skeleton   [5] their mask, then n_items items (lit_len | kind << 16 | op << 24), then 4 words of per-element tool-call flags when
-// tc_count > 0, then the skeleton runs (each starts on a word).
+constexpr uint32_t TF_HAS_USAGE = 1;
+constexpr uint32_t T_HDR = 7;              // header words
+enum : uint32_t { SK_LIT = 0, SK_WILD = 1, SK_LITINT = 2, SK_LIT3 = 3 };   // SK_LIT3: up to 3 bytes, held in the segment word itself
+// template in the store (32-bit words):
+//   [0] next | n_struct << 16          [1] skeleton bytes | flags << 16 | tc_count << 24     [2] static record flags
+//   [3] n_choices | n_ops << 16        [4],[5] bit j: structural stop j is '[' (else '"')
+//   [6] content segment | finish_reason segment << 8 (0xFF: none)
+//   n_struct + 1 segments: kind | len_a << 2 | len_b << 10 | byte offset into the literal pool << 18
+//   n_ops ops: code | segment << 8 | tool-call ordinal << 16
+//   4 words of per-element tool-call flags when tc_count > 0, then the literal pool
 
-// body of a string value from fp (just behind the opening quote): position of the closing quote, or SSE_NONE when the
-// body is not well formed (control byte, bad escape, no closing quote). d2 / done as the automaton would have them.
-__device__ __forceinline__ uint32_t t_scan_string(const FSmem &S, uint32_t fp, uint32_t pe, bool rmode, uint32_t &d2, bool &done) {
-    uint32_t p = fp;
-    for (;;) {
-        const uint32_t q = next_stop(S, p, pe);
-        if (q >= pe) return SSE_NONE;
-        const uint32_t c = S.tile[q];
-        if (c == '"') return q;
-        uint32_t adv = 0;
-        if (c == '\\') {
-            const uint32_t c2 = S.tile[q + 1u];
-            if (q + 2u <= pe && (c2 == '"' || c2 == '\\' || c2 == '/' || c2 == 'b' || c2 == 'f' || c2 == 'n' || c2 == 'r' || c2 == 't')) adv = 2;
-            else if (c2 == 'u' && q + 6u <= pe && hex4(S.tile + q + 2u) >= 0) adv = 6;
-            if (!adv) return SSE_NONE;
-            d2 |= 1u;
-        } else if (c == '[') {
-            if (rmode && q + 6u <= pe && is_done_at(S.tile + q)) done = true;
-            adv = 1;
-        } else if (c >= 0x80u) {
-            adv = (uint32_t)utf8_valid_len(S.tile + q, (int)(pe - q));
-            if (!adv) { adv = 1; d2 |= 2u; }        // invalid UTF-8: the automaton flags it (A_BAD_*) and goes on byte by byte
-        } else return SSE_NONE;                     // control byte
-        p = q + adv;
-        if (p >= pe) return SSE_NONE;
-    }
+__device__ __forceinline__ uint32_t store_load4(const FSmem &S, const uint32_t *pool, uint32_t off) {
+    const uint32_t *w = pool + (off >> 2);
+    return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
 }
-// integer from fp: [-] 0 | [1-9][0-9]*; returns its end, or SSE_NONE
-__device__ __forceinline__ uint32_t t_scan_int(const FSmem &S, uint32_t fp, uint32_t pe) {
-    uint32_t i = fp;
-    if (i < pe && S.tile[i] == '-') i++;
-    if (i >= pe) return SSE_NONE;
-    const uint32_t d0 = S.tile[i];
-    if (d0 == '0') return i + 1u;
-    if (d0 - '1' > 8u) return SSE_NONE;
-    i++;
-    while (i + 4u <= pe && nondigit4(load4(S, i)) == 0) i += 4u;
-    while (i < pe && (uint32_t)S.tile[i] - '0' <= 9u) i++;
-    return i;
+// line bytes [a, a+len) == pool bytes [off, off+len)
+__device__ __forceinline__ bool seg_equal(const FSmem &S, uint32_t a, const uint32_t *pool, uint32_t off, uint32_t len) {
+    if (len <= 4u) return len == 0u || ((load4(S, a) ^ store_load4(S, pool, off)) & (0xFFFFFFFFu >> ((4u - len) * 8u))) == 0u;
+    uint32_t diff = 0, j = 0;
+    #pragma unroll 1
+    for (; j + 4u <= len; j += 4u) diff |= load4(S, a + j) ^ store_load4(S, pool, off + j);
+    if (j < len) diff |= (load4(S, a + j) ^ store_load4(S, pool, off + j)) & ((1u << ((len - j) * 8u)) - 1u);
+    return diff == 0;
 }
-
-// Walk the line [ps, pe) along template T. APPLY = false: compare the skeleton and scan the wildcards, no side effects;
-// true: (after a successful compare) run the capture ops into the lane state. Returns false when the line does not fit.
-// SYNC: every lane of the warp is in the call (act: this lane has a line and a template); the lanes then meet after every
-// item -- without that, lanes that hold different templates drift apart and the warp executes them one after the other.
-template <bool APPLY, bool SYNC>
-__device__ __forceinline__ bool t_walk(const KParams &P, FSmem &S, FLane &L, const uint32_t *T, uint32_t ps, uint32_t pe,
-                                       uint32_t tc_base, uint32_t &tc_dyn, bool act = true) {
-    const uint32_t n_items = act ? T[3] >> 16 : 0u, tc_count = act ? T[1] >> 24 : 0u;
-    const uint32_t *items = T + T_HDR;
-    const uint32_t *lw = items + n_items + (tc_count ? 4u : 0u);
-    const bool rmode = (L.sf & SF_RMODE) != 0;
-    uint32_t fp = ps;
-    bool done = false, ok = act;
-    if (!APPLY && act) { L.content_pos = L.content_len = 0; L.finish = SSE_FIN_NONE; L.sf &= ~(SF_CDEC | SF_CBAD); }   // captures of an earlier candidate
-    for (uint32_t i = 0; ; i++) {
-        const bool go = ok && i < n_items;
-        if (SYNC) { if (!__any_sync(FULL, go)) break; } else if (!go) break;
-        if (go) {
-        const uint32_t it = items[i];
-        const uint32_t lit = it & 0xFFFFu, kind = (it >> 16) & 0xFFu, op = it >> 24;
-        if (!APPLY) {
-            uint32_t diff = fp + lit > pe ? 1u : 0u;
-            if (!diff) {
-                uint32_t j = 0;
-                for (; j + 4u <= lit; j += 4u) diff |= load4(S, fp + j) ^ lw[j >> 2];
-                if (j < lit) diff |= (load4(S, fp + j) ^ lw[j >> 2]) & ((1u << ((lit - j) * 8u)) - 1u);
-            }
-            if (diff) ok = false;
-        }
-        fp += lit; lw += (lit + 3u) >> 2;
-        if (kind == WK_END) { if (!APPLY && fp != pe) ok = false; }
-        else if (ok) {
-            uint32_t end, d2 = 0;
-            if (kind == WK_STR) end = t_scan_string(S, fp, pe, rmode, d2, done);
-            else end = t_scan_int(S, fp, pe);
-            if (end == SSE_NONE) ok = false;
-            else {
-                if (!APPLY && op != OP_NONE) {        // register-only captures are taken while comparing (TF_SIMPLE templates)
-                    const uint32_t code = op & 15u, len = end - fp;
-                    if (code == OP_CONTENT) {
-                        L.content_pos = fp; L.content_len = len;
-                        L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
-                    } else if (code == OP_FINISH) L.finish = f_match_finish(S, fp, len, d2);
-                    else if ((code == OP_CHK_I64 || code == OP_CHK_F32) && len > 18u) tc_dyn |= 0x80000000u;   // needs the range check of t_apply
-                }
-                if (APPLY && op != OP_NONE) {
-                    const uint32_t code = op & 15u, ord = op >> 4, len = end - fp;
-                    switch (code) {
-                    case OP_CONTENT:
-                        L.content_pos = fp; L.content_len = len;
-                        L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
-                        break;
-                    case OP_FINISH: L.finish = f_match_finish(S, fp, len, d2); break;
-                    case OP_TC_ID: case OP_TC_TYPE: case OP_TC_NAME: case OP_TC_ARGS:
-                        if (tc_base != SSE_NONE) {
-                            const uint32_t k = code - OP_TC_ID;
-                            sse_tc *t = &P.tcs[tc_base + ord];
-                            uint32_t *span = &t->id_off + 2u * k;
-                            f_cancel_job(S, span + 1);
-                            const Span sp = f_capture(P, S, L, fp, len, d2, span + 1);
-                            span[0] = sp.off; span[1] = sp.len;
-                            const uint32_t text_bit = SSE_TC_ID_TEXT << k;
-                            t->flags = (t->flags & ~text_bit) | (sp.text ? text_bit : 0u);
-                            if (k >= 2u) { const uint32_t b = 1u << (2u * ord + (k - 2u)); tc_dyn = len ? (tc_dyn | b) : (tc_dyn & ~b); }
-                        }
-                        break;
-                    case OP_TC_INDEX:
-                        L.sf |= f_number_value(P, S.tile, TY_INT, TG_TC_INDEX, fp, end, SSE_NONE, tc_base != SSE_NONE ? tc_base + ord : SSE_NONE);
-                        break;
-                    case OP_U_PROMPT: L.sf |= f_number_value(P, S.tile, TY_INT, TG_PROMPT, fp, end, L.usage_idx, SSE_NONE); break;
-                    case OP_U_COMPLETION: L.sf |= f_number_value(P, S.tile, TY_INT, TG_COMPLETION, fp, end, L.usage_idx, SSE_NONE); break;
-                    case OP_U_TOTAL: L.sf |= f_number_value(P, S.tile, TY_INT, TG_TOTAL, fp, end, L.usage_idx, SSE_NONE); break;
-                    case OP_CHK_I64: if (len > 18u) L.sf |= f_number_value(P, S.tile, TY_INT, TG_NONE, fp, end, SSE_NONE, SSE_NONE); break;
-                    case OP_CHK_F32: L.sf |= f_number_value(P, S.tile, TY_F32, TG_NONE, fp, end, SSE_NONE, SSE_NONE); break;
-                    default: break;
-                    }
-                }
-                fp = end;
-            }
-        }
-        }
-        if (SYNC) __syncwarp();
-    }
-    if (APPLY && done) L.sf |= SF_DONELINE;
-    if (!APPLY && done) tc_dyn |= 0x40000000u;
-    return ok;
+// integer [a, b): [-] 0 | [1-9][0-9]*
+__device__ __forceinline__ bool int_ok(const FSmem &S, uint32_t a, uint32_t b) {
+    if (a < b && S.tile[a] == '-') a++;
+    if (a >= b) return false;
+    const uint32_t d0 = S.tile[a];
+    if (d0 == '0') return a + 1u == b;
+    if (d0 - '1' > 8u) return false;
+    a++;
+    #pragma unroll 1
+    while (a + 4u <= b) { if (nondigit4(load4(S, a))) return false; a += 4u; }
+    if (a < b && (nondigit4(load4(S, a)) & (0xFFFFFFFFu >> ((4u - (b - a)) * 8u)))) return false;
+    return true;
+}
+__device__ __noinline__ bool escape_ok(const FSmem &S, uint32_t p, uint32_t pe) {      // p: an escaping backslash
+    const uint32_t c2 = S.tile[p + 1u];
+    if (p + 2u <= pe && (c2 == '"' || c2 == '\\' || c2 == '/' || c2 == 'b' || c2 == 'f' || c2 == 'n' || c2 == 'r' || c2 == 't')) return true;
+    return c2 == 'u' && p + 6u <= pe && hex4(S.tile + p + 2u) >= 0;
+}
+__device__ __noinline__ uint32_t backslash_run_before(const FSmem &S, uint32_t p, uint32_t lo) {
+    uint32_t n = 0;
+    while (p > lo && S.tile[p - 1u] == '\\') { n++; p--; }
+    return n;
 }
 
 __device__ __noinline__ uint32_t f_tcs_alloc(const KParams &P, uint32_t n, const uint32_t *static_flags) {
@@ -960,25 +893,6 @@ __device__ __noinline__ uint32_t f_tcs_alloc(const KParams &P, uint32_t n, const
         q[1] = make_uint4(0u, 0u, 0u, 0u); q[2] = make_uint4(0u, 0u, 0u, 0u);
     }
     return base;
-}
-
-// number of stop bytes the line would have if its strings were clean: 2 per string + '[' outside strings; SSE_NONE if a
-// string does not end
-__device__ __noinline__ uint32_t t_clean_key(const FSmem &S, uint32_t ps, uint32_t pe) {
-    uint32_t p = ps, n = 0;
-    bool in_str = false;
-    while (p < pe) {
-        const uint32_t q = next_stop(S, p, pe);
-        if (q >= pe) break;
-        const uint32_t c = S.tile[q];
-        p = q + 1u;
-        if (in_str) {
-            if (c == '"') { in_str = false; n += 2u; }
-            else if (c == '\\') p = q + 2u;
-        } else if (c == '"') in_str = true;
-        else if (c == '[') n++;
-    }
-    return in_str ? SSE_NONE : n;
 }
 
 // The record of a retired line (agent.go:205-242 reads) from the lane's final state. Out of line: called from the template
@@ -1022,8 +936,117 @@ __device__ __noinline__ void f_emit_record(const KParams &P, FSmem &S, uint32_t 
     if (terminates) atomicMin(&S.seg[ln.seg].term, line);
 }
 
+// does the string body [a, b) hold invalid UTF-8 (Go would write U+FFFD)? Escapes are skipped.
+__device__ __noinline__ bool body_has_bad_utf8(const FSmem &S, uint32_t a, uint32_t b) {
+    while (a < b) {
+        const uint32_t c = S.tile[a];
+        if (c == '\\') { a += 2u; continue; }
+        if (c < 0x80u) { a++; continue; }
+        const int k = utf8_valid_len(S.tile + a, (int)(b - a));
+        if (k == 0) return true;
+        a += (uint32_t)k;
+    }
+    return false;
+}
+
+// The automaton has just retired a line it recorded (slot rslot): turn the recording into a template.
 __device__ __noinline__ void t_build(const KParams &P, FSmem &S, uint32_t rslot, uint32_t ps, uint32_t pe, uint32_t rec_static,
-                                     uint32_t tflags, uint32_t n_choices, uint32_t tc_count, uint32_t tc_first);
+                                     uint32_t tflags, uint32_t n_choices, uint32_t tc_count, uint32_t tc_first) {
+    const FRec &R = S.rec[rslot];
+    if (tc_count > 15u || pe - ps < 2u) return;
+    const uint32_t off = S.ts_used;                     // built in place behind the last template (the caller holds the build lock)
+    if (off + 360u > (uint32_t)TS_WORDS) return;         // (a template is at most 7 + 65 + 24 + 4 + 257 words)
+    uint32_t *T = S.tstore + off;
+    uint32_t *segw = T + T_HDR;
+    // ---- the structural stops of the line, and what stands between them
+    uint32_t ns = 0, ev = 0, n_ops = 0, lit_used = 0, mask0 = 0, mask1 = 0, cseg = 0xFFu, fseg = 0xFFu;
+    uint32_t opw[24];
+    uint8_t lit[T_LIT_MAX];                             // (local scratch: building a template is rare)
+    uint32_t seg_a = ps;                                // first byte of the segment that is open
+    bool in_str = false, fail = false;
+    uint32_t p = ps;
+    for (;;) {
+        const uint32_t q = p < pe ? next_stop(S, p, pe) : pe;
+        const bool at_end = q >= pe;
+        uint32_t c = at_end ? 0u : (uint32_t)S.tile[q];
+        bool structural = at_end;
+        if (!at_end) {
+            if (in_str) { if (c == '"') structural = true; else if (c == '\\') { p = q + 2u; continue; } }
+            else if (c == '"' || c == '[') structural = true;
+            else { fail = true; break; }                // a stop byte outside strings that is not structural
+            if (!structural) { p = q + 1u; continue; }
+        }
+        // segment [seg_a, q)
+        const uint32_t a = seg_a, b = at_end ? pe : q, len = b - a;
+        uint32_t word;
+        if (ev < R.n && R.ev[ev].kind == WK_STR && R.ev[ev].start == a && (uint32_t)R.ev[ev].start + R.ev[ev].len == b && in_str) {
+            word = SK_WILD;
+            const uint32_t op = R.ev[ev].op, code = op & 15u;
+            if (code == OP_CONTENT) cseg = ns; else if (code == OP_FINISH) fseg = ns;
+            else if (code != OP_NONE) { if (n_ops < 24u) opw[n_ops++] = code | (ns << 8) | ((op >> 4) << 16); else fail = true; }
+            ev++;
+        } else if (ev < R.n && R.ev[ev].kind == WK_INT && R.ev[ev].start >= a && (uint32_t)R.ev[ev].start + R.ev[ev].len <= b && !in_str) {
+            const uint32_t ia = R.ev[ev].start, ib = ia + R.ev[ev].len, pre = ia - a, suf = b - ib;
+            if (pre > 255u || suf > 255u || lit_used + pre + suf > T_LIT_MAX) { fail = true; break; }
+            word = SK_LITINT | (pre << 2) | (suf << 10) | (lit_used << 18);
+            for (uint32_t i = 0; i < pre; i++) lit[lit_used++] = S.tile[a + i];
+            for (uint32_t i = 0; i < suf; i++) lit[lit_used++] = S.tile[ib + i];
+            const uint32_t op = R.ev[ev].op, code = op & 15u;
+            // (range checks are not ops: the replay leaves integers of more than 18 digits to the automaton)
+            if (code != OP_NONE && code != OP_CHK_I64 && code != OP_CHK_F32) { if (n_ops < 24u) opw[n_ops++] = code | (ns << 8) | ((op >> 4) << 16); else fail = true; }
+            ev++;
+            if (ev < R.n && R.ev[ev].start < b) { fail = true; break; }     // a second wildcard in the same segment
+        } else {
+            if (ev < R.n && R.ev[ev].start < b) { fail = true; break; }     // a wildcard that does not line up with a segment
+            if (len > 255u || lit_used + len > T_LIT_MAX) { fail = true; break; }
+            if (len <= 3u) {
+                word = SK_LIT3 | (len << 2);
+                for (uint32_t i = 0; i < len; i++) word |= (uint32_t)S.tile[a + i] << (8u + 8u * i);
+            } else {
+                word = SK_LIT | (len << 2) | (lit_used << 18);
+                for (uint32_t i = 0; i < len; i++) lit[lit_used++] = S.tile[a + i];
+            }
+        }
+        segw[ns] = word;
+        if (at_end) break;
+        if (ns >= 63u) { fail = true; break; }
+        if (c == '[') { if (ns < 32u) mask0 |= 1u << ns; else mask1 |= 1u << (ns - 32u); }
+        else in_str = !in_str;
+        ns++;
+        seg_a = q + 1u; p = q + 1u;
+    }
+    if (fail || in_str || ev != R.n) return;
+    const uint32_t n_struct = ns;
+    const uint32_t words = T_HDR + (n_struct + 1u) + n_ops + (tc_count ? 4u : 0u) + ((lit_used + 3u) >> 2) + 1u;
+    if (off + words > (uint32_t)TS_WORDS) return;
+    uint32_t *opsw = segw + n_struct + 1u, *tcs = opsw + n_ops, *pool = tcs + (tc_count ? 4u : 0u);
+    for (uint32_t i = 0; i < n_ops; i++) opsw[i] = opw[i];
+    if (tc_count) {
+        uint32_t w4[4] = { 0, 0, 0, 0 }, t = tc_first;
+        for (uint32_t j = 0; j < tc_count && t != SSE_NONE; j++) { w4[j >> 2] |= (P.tcs[t].flags & 7u) << ((j & 3u) * 8u); t = P.tcs[t].next; }
+        tcs[0] = w4[0]; tcs[1] = w4[1]; tcs[2] = w4[2]; tcs[3] = w4[3];
+    }
+    for (uint32_t i = 0; i < lit_used; i += 4u) {
+        uint32_t v = 0;
+        for (uint32_t b = 0; b < 4u && i + b < lit_used; b++) v |= (uint32_t)lit[i + b] << (8u * b);
+        pool[i >> 2] = v;
+    }
+    pool[(lit_used + 3u) >> 2] = 0;                        // (unaligned pool reads look one word ahead)
+    T[1] = lit_used | (tflags << 16) | (tc_count << 24); T[2] = rec_static; T[3] = n_choices | (n_ops << 16);
+    T[4] = mask0; T[5] = mask1; T[6] = cseg | (fseg << 8);
+    // the same skeleton may have been stored by another lane meanwhile: identical words
+    for (uint32_t o = S.thead[n_struct]; o; o = S.tstore[o] & 0xFFFFu) {
+        const uint32_t *U = S.tstore + o;
+        bool same = true;
+        for (uint32_t i = 1; i < words && same; i++) same = U[i] == T[i];
+        if (same) return;
+    }
+    T[0] = (n_struct << 16) | (S.thead[n_struct] & 0xFFFFu);
+    __threadfence_block();
+    S.ts_used = off + words;
+    S.thead[n_struct] = off;                               // published: readers see a complete template
+    PCOUNT(51, 1); PCOUNT(52, words);
+}
 
 // A line retires: final syntax check, record, termination bookkeeping (agent.go:205-242).
 __device__ __forceinline__ void f_finish_line(const KParams &P, FSmem &S, FLane &L) {
@@ -1043,15 +1066,8 @@ __device__ __forceinline__ void f_finish_line(const KParams &P, FSmem &S, FLane 
         const FRec &R = S.rec[L.rslot];
         // one lane builds at a time (a second one, most likely holding the same skeleton, just drops its recording)
         if (!R.nonsimple && !(L.sf & (SF_SYN | SF_TYPE | SF_DEPTH | SF_DONELINE)) && atomicCAS(&S.build_lock, 0u, 1u) == 0u) {
-            const uint32_t key = 2u * R.n_str + R.n_arr;
-            bool dup = false;        // another lane may have stored the same skeleton meanwhile
-            if (key < 255u)
-                for (uint32_t off = S.thead[key]; off && !dup; off = S.tstore[off] & 0xFFFFu) {
-                    uint32_t dummy = 0;
-                    dup = t_walk<false, false>(P, S, L, S.tstore + off, L.pe - L.plen, L.pe, SSE_NONE, dummy);
-                }
-            if (!dup) t_build(P, S, L.rslot, L.pe - L.plen, L.pe, SSE_F_JSON_OK | ((L.sf & SF_TCNONNIL) ? SSE_F_TC_NONNIL : 0u),
-                              ((L.sf & SF_USAGE) && L.usage_idx != SSE_NONE) ? TF_HAS_USAGE : 0u, L.n_choices, L.tc_count, L.tc_first);
+            t_build(P, S, L.rslot, L.pe - L.plen, L.pe, SSE_F_JSON_OK | ((L.sf & SF_TCNONNIL) ? SSE_F_TC_NONNIL : 0u),
+                    ((L.sf & SF_USAGE) && L.usage_idx != SSE_NONE) ? TF_HAS_USAGE : 0u, L.n_choices, L.tc_count, L.tc_first);
             __threadfence_block();
             atomicExch(&S.build_lock, 0u);
         }
@@ -1060,102 +1076,8 @@ __device__ __forceinline__ void f_finish_line(const KParams &P, FSmem &S, FLane 
     }
 }
 
-// run template T's capture ops for the lane's line (its skeleton has just compared equal) and retire the line
-__device__ __forceinline__ void t_apply(const KParams &P, FSmem &S, FLane &L, const uint32_t *T, bool act) {
-    if (!act) { uint32_t d = 0; t_walk<true, true>(P, S, L, T, 0, 0, SSE_NONE, d, false); return; }
-    const uint32_t n_items = T[3] >> 16, tc_count = T[1] >> 24, tflags = (T[1] >> 16) & 0xFFu;
-    const uint32_t *tc_static = T + T_HDR + n_items;
-    uint32_t tc_base = SSE_NONE, tc_dyn = 0;
-    if (tflags & TF_HAS_USAGE) { L.usage_idx = f_usage_alloc(P); L.sf |= SF_USAGE; }
-    if (tc_count) tc_base = f_tcs_alloc(P, tc_count, tc_static);
-    L.finish = SSE_FIN_NONE; L.content_pos = L.content_len = 0;
-    t_walk<true, true>(P, S, L, T, L.p, L.pe, tc_base, tc_dyn, true);
-    L.n_choices = T[3] & 0xFFFFu;
-    if (T[2] & SSE_F_TC_NONNIL) L.sf |= SF_TCNONNIL;
-    L.tc_count = tc_base != SSE_NONE ? tc_count : 0u; L.tc_first = tc_base;
-    const uint8_t *st8 = reinterpret_cast<const uint8_t *>(tc_static);
-    for (uint32_t j = 0; j < tc_count; j++)
-        if ((st8[j] & SSE_TC_HAS_ID) || ((st8[j] & SSE_TC_HAS_FUNC) && ((tc_dyn >> (2u * j)) & 3u))) L.sf |= SF_TCVALID;
-    L.st = S_END; L.depth = 0; L.p = L.pe;
-    f_finish_line(P, S, L);
-}
-// Walk the chains: every lane of the warp tries its next candidate in the same iteration (the loop condition is
-// warp-uniform), so lanes that need more attempts do not fall out of step with the others. off: first candidate per lane
-// (0: none). Returns the template that fits (0: none).
-__device__ __forceinline__ uint32_t t_find(const KParams &P, FSmem &S, FLane &L, uint32_t off, uint32_t &vflags) {
-    uint32_t found = 0;
-    const uint32_t tail = L.plen >= 4u ? load4(S, L.pe - 4u) : 0u;
-    while (__any_sync(FULL, off != 0u)) {
-        // candidates whose last skeleton bytes differ from the line's are passed over right here
-        while (off && (L.plen < 4u || ((tail ^ S.tstore[off + 4u]) & S.tstore[off + 5u]))) off = S.tstore[off] & 0xFFFFu;
-        const uint32_t *T = S.tstore + off;
-        uint32_t vf = 0;
-        if (off) PCOUNT(48, 1);
-        const bool fit = t_walk<false, true>(P, S, L, T, L.p, L.pe, SSE_NONE, vf, off != 0u);
-        if (off) {
-            if (fit) { PCOUNT(49, 1); found = off; off = 0; vflags = vf; }
-            else off = T[0] & 0xFFFFu;
-        }
-    }
-    return found;
-}
-
-// The automaton has just retired a line it recorded (slot rslot): turn the recording into a template.
-__device__ __noinline__ void t_build(const KParams &P, FSmem &S, uint32_t rslot, uint32_t ps, uint32_t pe, uint32_t rec_static,
-                                     uint32_t tflags, uint32_t n_choices, uint32_t tc_count, uint32_t tc_first) {
-    const FRec &R = S.rec[rslot];
-    const uint32_t key = 2u * R.n_str + R.n_arr;
-    if (key >= 255u || tc_count > 15u) return;
-    const uint32_t n_items = (uint32_t)R.n + 1u;
-    uint32_t prev = ps, litw = 0, litb = 0;
-    for (uint32_t i = 0; i < R.n; i++) {
-        const uint32_t s = R.ev[i].start, e = s + R.ev[i].len;
-        if (s < prev || e > pe) return;
-        litw += (s - prev + 3u) >> 2; litb += s - prev; prev = e;
-    }
-    litw += (pe - prev + 3u) >> 2; litb += pe - prev;
-    if (litb > T_LIT_MAX) return;
-    const uint32_t words = T_HDR + n_items + (tc_count ? 4u : 0u) + litw;
-    const uint32_t off = atomicAdd(&S.ts_used, words);
-    if (off + words > (uint32_t)TS_WORDS) { atomicSub(&S.ts_used, words); return; }
-    uint32_t *T = S.tstore + off;
-    {
-        const uint32_t endlit = pe - prev;                       // skeleton bytes behind the last wildcard: a cheap first test
-        const uint32_t tn = min(endlit, 4u);
-        const uint32_t tmask = tn == 4u ? 0xFFFFFFFFu : tn == 0u ? 0u : ~((1u << ((4u - tn) * 8u)) - 1u);     // the high tn bytes of load4(pe - 4)
-        T[4] = pe - ps >= 4u ? (load4(S, pe - 4u) & tmask) : 0u; T[5] = pe - ps >= 4u ? tmask : 0u;
-        bool simple = !(tflags & TF_HAS_USAGE) && tc_count == 0;
-        for (uint32_t i = 0; i < R.n; i++) { const uint32_t c = R.ev[i].op & 15u; if (c != OP_NONE && c != OP_CONTENT && c != OP_FINISH && c != OP_CHK_I64 && c != OP_CHK_F32) simple = false; }
-        if (simple) tflags |= TF_SIMPLE;
-    }
-    T[0] = key << 16; T[1] = litb | (tflags << 16) | (tc_count << 24); T[2] = rec_static; T[3] = n_choices | (n_items << 16);
-    uint32_t *items = T + T_HDR, *tcs = items + n_items, *lw = tcs + (tc_count ? 4u : 0u);
-    if (tc_count) {
-        uint32_t w4[4] = { 0, 0, 0, 0 }, t = tc_first;
-        for (uint32_t j = 0; j < tc_count && t != SSE_NONE; j++) { w4[j >> 2] |= (P.tcs[t].flags & 7u) << ((j & 3u) * 8u); t = P.tcs[t].next; }
-        tcs[0] = w4[0]; tcs[1] = w4[1]; tcs[2] = w4[2]; tcs[3] = w4[3];
-    }
-    prev = ps;
-    for (uint32_t i = 0; i < n_items; i++) {
-        const bool last = i + 1u == n_items;
-        const uint32_t s = last ? pe : (uint32_t)R.ev[i].start;
-        const uint32_t lit = s - prev;
-        items[i] = lit | ((last ? (uint32_t)WK_END : (uint32_t)R.ev[i].kind) << 16) | ((last ? 0u : (uint32_t)R.ev[i].op) << 24);
-        for (uint32_t j = 0; j < lit; j += 4u) {
-            uint32_t v = load4(S, prev + j);
-            if (lit - j < 4u) v &= (1u << ((lit - j) * 8u)) - 1u;
-            *lw++ = v;
-        }
-        prev = last ? pe : s + R.ev[i].len;
-    }
-    PCOUNT(51, 1); PCOUNT(52, words);
-    __threadfence_block();
-    const uint32_t old = atomicExch(&S.thead[key], off);      // published: readers see a complete template
-    T[0] = (key << 16) | (old & 0xFFFFu);
-}
-
-// lane state for the line of decode job j (everything both paths need)
-__device__ __forceinline__ uint32_t lane_setup(const KParams &P, const FSmem &S, FLane &L, uint32_t j, uint32_t rb) {
+// lane state for the line of decode job j
+__device__ __forceinline__ void lane_setup(const KParams &P, const FSmem &S, FLane &L, uint32_t j, uint32_t rb) {
     const uint32_t k = S.job[j];
     const FLine ln = S.line[k];
     const FSeg &sg = S.seg[ln.seg];
@@ -1170,55 +1092,224 @@ __device__ __forceinline__ uint32_t lane_setup(const KParams &P, const FSmem &S,
     L.content_pos = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = L.tc_cur = SSE_NONE; L.tcb = 0;
     L.usage_idx = SSE_NONE; L.rslot = SSE_NONE;
     L.busy = true;
-    return ln.pad;
 }
 
-// Template path of stage 2 for one pass of jobs (own function: its registers are not the automaton's). Every lane of the
-// warp calls it; has: the lane holds job j. Returns true when the lane's line was retired through a template.
-__device__ __noinline__ bool stage2_replay(const KParams &P, FSmem &S, bool has, uint32_t j, uint32_t rb) {
-    FLane L;
-    L.busy = false; L.p = L.pe = 0; L.plen = 0; L.sf = 0; L.rslot = SSE_NONE; L.line = 0; L.rec = 0; L.delta = 0;
-    L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.slen = 0; L.choices_count = L.n_choices = 0; L.finish = 0;
-    L.ct = L.ct1 = L.sstk = 0; L.content_pos = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = L.tc_cur = SSE_NONE;
-    L.tcb = 0; L.usage_idx = SSE_NONE;
-#ifdef SSE_PROF
-    long long ts_ = clock64();
-#endif
-    uint32_t key = 255u;
-    if (has) key = lane_setup(P, S, L, j, rb);
-    // swallowed "[DONE]" lines go to the automaton: their flag is not part of a template
-    const bool cand = has && !(L.sf & SF_DONELINE);
-    PSTAMP(0);
-    uint32_t vflags = 0, toff = 0;
-    uint32_t first = (cand && key < 255u) ? S.thead[key] : 0u;
-    #pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-        const uint32_t f = t_find(P, S, L, first, vflags);
-        if (f) toff = f;
-        // escapes and non-ASCII bytes in string values add stop bytes: look under the clean count too
-        const bool miss = cand && !toff && pass == 0;
-        if (!__any_sync(FULL, miss)) break;
-        const uint32_t key2 = miss ? t_clean_key(S, L.p, L.pe) : 255u;
-        first = (miss && key2 < 255u && key2 != key) ? S.thead[key2] : 0u;
-        PSTAMP(1);
-    }
-    PSTAMP(2);
-    {   // the record is written, the lane retires
-        const uint32_t *T = S.tstore + toff;
-        const bool simple = toff && ((T[1] >> 16) & TF_SIMPLE) && !(vflags & 0x80000000u);
-        if (simple) {                                    // everything was captured while comparing
-            if (vflags & 0x40000000u) L.sf |= SF_DONELINE;
-            L.n_choices = T[3] & 0xFFFFu;
-            if (T[2] & SSE_F_TC_NONNIL) L.sf |= SF_TCNONNIL;
-            L.st = S_END; L.depth = 0; L.p = L.pe;
-            f_finish_line(P, S, L);
+// A template with usage / tool-call / range-check ops has fitted (rare lines: first tool-call chunk, usage chunk): one lane
+// runs the ops and writes the record. Out of line: not part of the steady-state code.
+__device__ __noinline__ void replay_ops(const KParams &P, FSmem &S, FWarp &W, const uint16_t *SS, bool clean, const uint32_t *T, uint32_t k, uint32_t j, uint32_t rb,
+                                        uint32_t ps, uint32_t pe, uint32_t n_struct, uint32_t cpos, uint32_t clen, uint32_t d2, uint32_t fin, bool done) {
+    const FLine ln = S.line[k];
+    const bool rmode = (ln.flags & LF_RMODE) != 0;
+    const uint32_t n_ops = T[3] >> 16, tc_count = T[1] >> 24, tflags = (T[1] >> 16) & 0xFFu;
+    const FSeg &sg = S.seg[ln.seg];
+    const uint32_t src_s = rmode ? ln.a : ln.start;
+    const uint32_t delta = (ln.flags & LF_ZC) ? P.in_base + sg.in_delta : ln.out_off - src_s;
+    uint32_t sf = (rmode ? SF_RMODE : 0u) | (done ? SF_DONELINE : 0u) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
+    uint32_t usage_idx = SSE_NONE, tc_base = SSE_NONE, tc_dyn = 0;
+    const uint32_t *opsw = T + T_HDR + n_struct + 1u, *tc_static = opsw + n_ops;
+    if (tflags & TF_HAS_USAGE) { usage_idx = f_usage_alloc(P); sf |= SF_USAGE; }
+    if (tc_count) tc_base = f_tcs_alloc(P, tc_count, tc_static);
+    FLane C; C.delta = delta;
+    for (uint32_t i = 0; i < n_ops; i++) {
+        const uint32_t code = opsw[i] & 0xFFu, s = (opsw[i] >> 8) & 0xFFu, ord = opsw[i] >> 16;
+        uint32_t a = s == 0 ? ps : (uint32_t)SS[s - 1u] + 1u, b = s == n_struct ? pe : (uint32_t)SS[s];
+        if (code >= OP_TC_INDEX) {                    // an integer: inside the segment's punctuation
+            const uint32_t sw = T[T_HDR + s];
+            a += (sw >> 2) & 0xFFu; b -= (sw >> 10) & 0xFFu;
         }
-        const bool full = toff && !simple;               // usage / tool-call / range-check ops: a second walk
-        if (__any_sync(FULL, full)) t_apply(P, S, L, T, full);
+        switch (code) {
+        case OP_TC_ID: case OP_TC_TYPE: case OP_TC_NAME: case OP_TC_ARGS:
+            if (tc_base != SSE_NONE) {
+                const uint32_t kf = code - OP_TC_ID, dd = clean ? 0u : (W.sdirty[s >> 2] >> ((s & 3u) * 8u)) & 0xFFu;
+                const uint32_t e2 = (dd & 1u) | (((dd & 2u) && body_has_bad_utf8(S, a, b)) ? 2u : 0u);
+                sse_tc *t = &P.tcs[tc_base + ord];
+                uint32_t *span = &t->id_off + 2u * kf;
+                f_cancel_job(S, span + 1);
+                const Span sp = f_capture(P, S, C, a, b - a, e2, span + 1);
+                span[0] = sp.off; span[1] = sp.len;
+                const uint32_t text_bit = SSE_TC_ID_TEXT << kf;
+                t->flags = (t->flags & ~text_bit) | (sp.text ? text_bit : 0u);
+                if (kf >= 2u) { const uint32_t bb = 1u << (2u * ord + (kf - 2u)); tc_dyn = (b > a) ? (tc_dyn | bb) : (tc_dyn & ~bb); }
+            }
+            break;
+        case OP_TC_INDEX: sf |= f_number_value(P, S.tile, TY_INT, TG_TC_INDEX, a, b, SSE_NONE, tc_base != SSE_NONE ? tc_base + ord : SSE_NONE); break;
+        case OP_U_PROMPT: sf |= f_number_value(P, S.tile, TY_INT, TG_PROMPT, a, b, usage_idx, SSE_NONE); break;
+        case OP_U_COMPLETION: sf |= f_number_value(P, S.tile, TY_INT, TG_COMPLETION, a, b, usage_idx, SSE_NONE); break;
+        case OP_U_TOTAL: sf |= f_number_value(P, S.tile, TY_INT, TG_TOTAL, a, b, usage_idx, SSE_NONE); break;
+        case OP_CHK_I64: if (b - a > 18u) sf |= f_number_value(P, S.tile, TY_INT, TG_NONE, a, b, SSE_NONE, SSE_NONE); break;
+        case OP_CHK_F32: if (b - a > 18u) sf |= f_number_value(P, S.tile, TY_F32, TG_NONE, a, b, SSE_NONE, SSE_NONE); break;
+        default: break;
+        }
     }
-    PSTAMP(3);
-    if (cand && !toff) PCOUNT(50, 1);
-    return toff != 0;
+    if (T[2] & SSE_F_TC_NONNIL) sf |= SF_TCNONNIL;
+    const uint8_t *st8 = reinterpret_cast<const uint8_t *>(tc_static);
+    for (uint32_t q = 0; q < tc_count; q++)
+        if ((st8[q] & SSE_TC_HAS_ID) || ((st8[q] & SSE_TC_HAS_FUNC) && ((tc_dyn >> (2u * q)) & 3u))) sf |= SF_TCVALID;
+    f_emit_record(P, S, sf, T[3] & 0xFFFFu, usage_idx, cpos, clen, fin, tc_base != SSE_NONE ? tc_count : 0u, tc_base, rb + ln.rank_r,
+                  pe - ps, k, delta);
+    FRes rs; rs.cpos = rs.clen = rs.toff = 0; rs.misc = 128u;      // done: nothing left for the record pass
+    S.res[j] = rs;
+}
+
+// ---- warp-per-line replay
+// One warp, one line. Returns true when a template fitted: the line's captures are then in S.res[job] (content and
+// finish_reason only) for the lane-per-line record pass, or -- templates with usage / tool-call / range-check ops -- the
+// record has been written right here by lane 0.
+__device__ __noinline__ bool warp_replay(const KParams &P, FSmem &S, uint32_t j, uint32_t rb) {
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    FWarp &W = S.wsc[wid];
+    const uint32_t k = S.job[j];
+    const FLine ln = S.line[k];
+    if (ln.flags & LF_DONE) return false;         // swallowed "[DONE]" lines: their flag is not part of a template
+    const uint32_t ps = (ln.flags & LF_PREF) ? ln.a + 6u : ln.a, pe = ln.b;
+    const bool rmode = (ln.flags & LF_RMODE) != 0;
+    if (pe <= ps) return false;
+    // ---- 1. the stop bytes of the payload, in order
+    uint32_t n_stops = 0;
+    const uint32_t w_end = (pe - 1u) >> 5;
+    #pragma unroll 1
+    for (uint32_t wb = ps >> 5; wb <= w_end; wb += 32u) {
+        const uint32_t w = wb + lane;
+        uint32_t bits = w <= w_end ? S.stopbm[w] : 0u;
+        const uint32_t wpos = w << 5;
+        if (wpos < ps) bits &= 0xFFFFFFFFu << (ps - wpos);
+        if (w == w_end && (pe & 31u)) bits &= (1u << (pe & 31u)) - 1u;
+        const uint32_t cnt = __popc(bits), incl = warp_incl(cnt, lane);
+        uint32_t base = n_stops + incl - cnt;
+        #pragma unroll
+        for (int q = 0; q < 3; q++)                    // (a 32-byte word rarely holds more than three stops)
+            if (bits) {
+                const uint32_t b = (uint32_t)__ffs(bits) - 1u;
+                bits &= bits - 1u;
+                if (base < (uint32_t)W_STOPS) W.spos[base] = (uint16_t)(wpos + b);
+                base++;
+            }
+        #pragma unroll 1
+        while (bits) {
+            const uint32_t b = (uint32_t)__ffs(bits) - 1u;
+            bits &= bits - 1u;
+            if (base < (uint32_t)W_STOPS) W.spos[base] = (uint16_t)(wpos + b);
+            base++;
+        }
+        n_stops += __shfl_sync(FULL, incl, 31);
+    }
+    if (n_stops > (uint32_t)W_STOPS) return false;
+    __syncwarp();
+    // ---- 2a. the usual line: every stop is a quote or a '[' outside strings -- all of them structural, nothing to validate
+    const uint16_t *SS = W.spos;
+    bool clean = true;
+    {
+        uint32_t par = 0;
+        bool odd = false;
+        #pragma unroll 1
+        for (uint32_t r0 = 0; r0 < n_stops; r0 += 32u) {
+            const uint32_t i = r0 + lane;
+            const bool have = i < n_stops;
+            const uint32_t c = have ? (uint32_t)S.tile[W.spos[i]] : (uint32_t)'"';
+            const unsigned qm = __ballot_sync(FULL, have && c == '"');
+            const bool inside = ((par + __popc(qm & lt)) & 1u) != 0;
+            if (have && c != '"' && (c != '[' || inside)) odd = true;
+            par ^= __popc(qm) & 1u;
+        }
+        clean = !__any_sync(FULL, odd) && !par && n_stops <= (uint32_t)W_STRUCT;
+    }
+    uint32_t parity = 0, n_struct = clean ? n_stops : 0u;
+    bool bad = false, done = false;
+    if (!clean) {
+    SS = W.sstop;
+    if (lane < (uint32_t)(W_STRUCT + 8) / 4u) W.sdirty[lane] = 0;
+    __syncwarp();
+    // ---- 2b. which stops are structural (string parity by ballot); are the others harmless?
+    #pragma unroll 1
+    for (uint32_t r0 = 0; r0 < n_stops; r0 += 32u) {
+        const uint32_t i = r0 + lane;
+        const bool have = i < n_stops;
+        const uint32_t p = have ? (uint32_t)W.spos[i] : ps;
+        const uint32_t c = have ? (uint32_t)S.tile[p] : 0u;
+        uint32_t run = 0;
+        if (have && (c == '"' || c == '\\') && p > ps && S.tile[p - 1u] == '\\') run = backslash_run_before(S, p, ps);
+        const bool is_q = have && c == '"' && !(run & 1u);
+        const unsigned qm = __ballot_sync(FULL, is_q);
+        const bool inside = ((parity + __popc(qm & lt)) & 1u) != 0;       // inside a string before this stop
+        const bool brk = have && c == '[' && !inside;
+        const unsigned sm = __ballot_sync(FULL, is_q || brk);
+        const uint32_t segi = n_struct + __popc(sm & lt);                  // structural stops before this one = its segment
+        if (have && !is_q && !brk) {
+            if (!inside) bad = true;                                       // a stray byte between tokens: the automaton's business
+            else if (c < 0x20u) bad = true;
+            else if (c == '\\') {
+                if (!(run & 1u) && !escape_ok(S, p, pe)) bad = true;      // an escaping backslash: what follows must be an escape
+                if (segi < (uint32_t)W_STRUCT + 2u) atomicOr(&W.sdirty[segi >> 2], 1u << ((segi & 3u) * 8u));
+            } else if (c >= 0x80u) { if (segi < (uint32_t)W_STRUCT + 2u) atomicOr(&W.sdirty[segi >> 2], 2u << ((segi & 3u) * 8u)); }
+            else if (c == '[') { if (rmode && p + 6u <= pe && is_done_at(S.tile + p)) done = true; }
+        }
+        if (is_q || brk) { if (segi < (uint32_t)W_STRUCT) W.sstop[segi] = (uint16_t)p; }
+        n_struct += __popc(sm);
+        parity ^= __popc(qm) & 1u;
+    }
+    if (__any_sync(FULL, bad) || parity || n_struct > (uint32_t)W_STRUCT) return false;
+    done = __any_sync(FULL, done);
+    __syncwarp();
+    }
+    // ---- 3. a template with these structural stops and segments?
+    uint32_t off = S.thead[n_struct];
+    const uint32_t *T = nullptr;
+    #pragma unroll 1
+    for (; off; off = S.tstore[off] & 0xFFFFu) {
+        const uint32_t *U = S.tstore + off;
+        const uint32_t *segw = U + T_HDR;
+        const uint32_t n_ops = U[3] >> 16, tc_count = U[1] >> 24;
+        const uint32_t *pool = segw + n_struct + 1u + n_ops + (tc_count ? 4u : 0u);
+        bool ok = true;
+        #pragma unroll 1
+        for (uint32_t s0 = 0; s0 <= n_struct; s0 += 32u) {
+            const uint32_t s = s0 + lane;
+            if (s <= n_struct) {
+                const uint32_t a = s == 0 ? ps : (uint32_t)SS[s - 1u] + 1u, b = s == n_struct ? pe : (uint32_t)SS[s], len = b - a;
+                if (s < n_struct) {
+                    const uint32_t isb = S.tile[b] == '[' ? 1u : 0u;
+                    if (isb != (((s < 32u ? U[4] : U[5]) >> (s & 31u)) & 1u)) ok = false;
+                }
+                const uint32_t sw = segw[s], kind = sw & 3u, la = (sw >> 2) & 0xFFu, lb = (sw >> 10) & 0xFFu, lo = sw >> 18;
+                if (kind == SK_LIT3) {
+                    const uint32_t l3 = (sw >> 2) & 3u;
+                    if (len != l3 || (l3 && ((load4(S, a) ^ (sw >> 8)) & (0xFFFFFFu >> ((3u - l3) * 8u))))) ok = false;
+                }
+                else if (kind == SK_LIT) { if (len != la || !seg_equal(S, a, pool, lo, la)) ok = false; }
+                else if (kind == SK_LITINT) {     // (an integer of more than 18 digits needs a range check: the automaton's business)
+                    if (len <= la + lb || len > la + lb + 18u || !seg_equal(S, a, pool, lo, la) || !seg_equal(S, b - lb, pool, lo + la, lb) || !int_ok(S, a + la, b - lb)) ok = false;
+                }
+            }
+        }
+        if (__all_sync(FULL, ok)) { T = U; break; }
+    }
+    if (!T) return false;
+    if (lane == 0) PCOUNT(49, 1);
+    // ---- 4. the captures
+    const uint32_t cseg = T[6] & 0xFFu, fseg = (T[6] >> 8) & 0xFFu, n_ops = T[3] >> 16, tc_count = T[1] >> 24, tflags = (T[1] >> 16) & 0xFFu;
+    if (lane == 0) {
+        uint32_t cpos = 0, clen = 0, d2 = 0, fin = SSE_FIN_NONE;
+        if (cseg != 0xFFu) {
+            cpos = (uint32_t)SS[cseg - 1u] + 1u; clen = (uint32_t)SS[cseg] - cpos;
+            const uint32_t dd = clean ? 0u : (W.sdirty[cseg >> 2] >> ((cseg & 3u) * 8u)) & 0xFFu;
+            d2 = (dd & 1u) | (((dd & 2u) && body_has_bad_utf8(S, cpos, cpos + clen)) ? 2u : 0u);
+        }
+        if (fseg != 0xFFu) {
+            const uint32_t fp = (uint32_t)SS[fseg - 1u] + 1u, fl = (uint32_t)SS[fseg] - fp;
+            const uint32_t dd = clean ? 0u : (W.sdirty[fseg >> 2] >> ((fseg & 3u) * 8u)) & 0xFFu;
+            fin = f_match_finish(S, fp, fl, dd ? 1u : 0u);
+        }
+        if (n_ops == 0 && !(tflags & TF_HAS_USAGE) && tc_count == 0) {
+            FRes rs; rs.cpos = (uint16_t)cpos; rs.clen = (uint16_t)clen; rs.toff = (uint16_t)(T - S.tstore);
+            rs.misc = (uint16_t)(d2 | (fin << 2) | (done ? 32u : 0u) | 64u);
+            S.res[j] = rs;
+        } else {
+            replay_ops(P, S, W, SS, clean, T, k, j, rb, ps, pe, n_struct, cpos, clen, d2, fin, done);
+        }
+    }
+    __syncwarp();
+    return true;
 }
 
 // Automaton path of stage 2: the lanes whose line no template took.
@@ -1230,7 +1321,7 @@ __device__ __noinline__ void stage2_automaton(const KParams &P, FSmem &S, bool h
     L.tcb = 0; L.usage_idx = SSE_NONE;
     if (has) {
         lane_setup(P, S, L, j, rb);
-        if (!(P.flags & SSE_FLAG_NO_TEMPLATES) && !(L.sf & SF_DONELINE) && S.ts_used + 128u < (uint32_t)TS_WORDS) {
+        if (!(P.flags & SSE_FLAG_NO_TEMPLATES) && !(L.sf & SF_DONELINE) && S.ts_used + 360u <= (uint32_t)TS_WORDS) {
             uint32_t m = S.rec_busy;                 // record a template while the automaton walks the line
             while ((~m) & ((1u << NREC) - 1u)) {
                 const uint32_t b = (uint32_t)__ffs((~m) & ((1u << NREC) - 1u)) - 1u;
@@ -1249,30 +1340,46 @@ __device__ __noinline__ void stage2_automaton(const KParams &P, FSmem &S, bool h
     }
 }
 
+// Stage 2 of a round: (a) every warp takes lines one at a time through the templates; (b) the lines no template took go
+// through the automaton, one lane per line; (c) after a block barrier (process_window) one thread per line writes the records
+// of the lines whose captures (a) left in S.res.
 __device__ void stage2(const KParams &P, FSmem &S, uint32_t n_jobs, uint32_t rb) {
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < n_jobs; base += F_THREADS) {
-        const uint32_t left = min(n_jobs - base, (uint32_t)F_THREADS);
-#ifndef SSE_LPW
-#define SSE_LPW 32
-#endif
-        // SSE_LPW consecutive jobs (lines of the same streams: the same templates) per warp
-        const uint32_t lpw = max(min((uint32_t)SSE_LPW, 32u), (left + F_WARPS - 1u) / F_WARPS);
-        if (wid * lpw >= left) break;                        // no line for this warp (warp-uniform)
-        const uint32_t j = lane < lpw ? base + wid * lpw + lane : n_jobs;
-        const bool has = j < n_jobs;
-        bool todo = has;
-        if (!(P.flags & SSE_FLAG_NO_TEMPLATES)) {
-            const bool hit = stage2_replay(P, S, has, j, rb);      // (every lane makes the call: it holds warp-wide votes)
-            todo = has && !hit;
-        }
-        if (__any_sync(FULL, todo)) stage2_automaton(P, S, todo, j, rb);
+    #pragma unroll 1
+    for (uint32_t j = wid; j < n_jobs; j += F_WARPS) {
+        bool hit = false;
+        if (!(P.flags & SSE_FLAG_NO_TEMPLATES)) hit = warp_replay(P, S, j, rb);
+        if (!hit && lane == 0) { PCOUNT(50, 1); FRes z; z.cpos = z.clen = z.toff = 0; z.misc = 0; S.res[j] = z; }
+    }
+    __syncwarp();
+    // the lines no template took: lane i has this warp's i-th line
+    const uint32_t mj = wid + F_WARPS * lane;
+    const bool miss = mj < n_jobs && S.res[mj].misc == 0;
+    if (__any_sync(FULL, miss)) stage2_automaton(P, S, miss, mj, rb);
+}
+
+// (c): records of the lines whose template captures are content / finish_reason only. One thread per job.
+__device__ __forceinline__ void stage2_records(const KParams &P, FSmem &S, uint32_t n_jobs, uint32_t rb) {
+    for (uint32_t j = threadIdx.x; j < n_jobs; j += F_THREADS) {
+        const FRes rs = S.res[j];
+        if (!(rs.misc & 64u)) continue;
+        const uint32_t k = S.job[j];
+        const FLine ln = S.line[k];
+        const FSeg &sg = S.seg[ln.seg];
+        const bool rmode = (ln.flags & LF_RMODE) != 0;
+        const uint32_t ps = (ln.flags & LF_PREF) ? ln.a + 6u : ln.a, src_s = rmode ? ln.a : ln.start;
+        const uint32_t delta = (ln.flags & LF_ZC) ? P.in_base + sg.in_delta : ln.out_off - src_s;
+        const uint32_t *T = S.tstore + rs.toff;
+        const uint32_t d2 = rs.misc & 3u;
+        const uint32_t sf = (rmode ? SF_RMODE : 0u) | ((rs.misc & 32u) ? SF_DONELINE : 0u) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u) |
+                            ((T[2] & SSE_F_TC_NONNIL) ? SF_TCNONNIL : 0u);
+        f_emit_record(P, S, sf, T[3] & 0xFFFFu, SSE_NONE, rs.cpos, rs.clen, (rs.misc >> 2) & 7u, 0u, SSE_NONE, rb + ln.rank_r, ln.b - ps, k, delta);
     }
 }
 
 // ---------------------------------------------------------------- one window of the tile: stage 1a .. finish of its rounds
 // S.seg[0..nseg) describe the regions; fill = end of the last region. Returns through the segment table.
-__device__ void process_window(const KParams &P, FSmem &S, uint32_t first_seg, uint32_t nseg, uint32_t fill) {
+__device__ __noinline__ void process_window(const KParams &P, FSmem &S, uint32_t first_seg, uint32_t nseg, uint32_t fill) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const bool zero_copy = !(P.flags & SSE_FLAG_COPY_OUT);
     PROF(0);
@@ -1281,6 +1388,7 @@ __device__ void process_window(const KParams &P, FSmem &S, uint32_t first_seg, u
     PROF(1);
 
     uint32_t r_start = 0;
+    #pragma unroll 1
     for (;;) {   // rounds of up to LCAP lines
         // ---------------- stage 1b: newline bits of this thread's 128 bytes, line table
         uint32_t nlm[4], cnt = 0;
@@ -1303,6 +1411,7 @@ __device__ void process_window(const KParams &P, FSmem &S, uint32_t first_seg, u
             for (int j = 0; j < 4; j++) {
                 uint32_t m = nlm[j];
                 const uint32_t wpos = (tid * 4u + (uint32_t)j) << 5;
+                #pragma unroll 1
                 while (m) {
                     const uint32_t b = (uint32_t)__ffs(m) - 1u;
                     m &= m - 1u;
@@ -1323,6 +1432,7 @@ __device__ void process_window(const KParams &P, FSmem &S, uint32_t first_seg, u
         if (k < n_lines) {
             const uint32_t nl = S.line[k].nl;
             uint32_t lo = 0, hi = nseg;             // last segment with data_off <= nl
+            #pragma unroll 1
             while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (S.seg[mid].data_off <= nl) lo = mid; else hi = mid; }
             my_seg = lo;
             const FSeg &sg = S.seg[lo];
@@ -1335,7 +1445,7 @@ __device__ void process_window(const KParams &P, FSmem &S, uint32_t first_seg, u
             else if (nl - start > P.carry_slot) { atomicMin(&S.seg[lo].dead, k); kind = K_DROP; }
             else if (mode & SSE_MODE_R) {
                 lflags |= LF_RMODE;
-                trim_space(S.tile, a, b);                                          // agent.go:178-179
+                { const uint32_t ab = trim_space_ab(S.tile, (uint32_t)a, (uint32_t)b); a = (int)(ab & 0xFFFFu); b = (int)(ab >> 16); }   // agent.go:178-179
                 const bool pref = is_data_prefix(S.tile + a, b - a);               // agent.go:186
                 if (pref && b - a > 6) {                                           // agent.go:190-197; "[DONE]" is found by the decoder
                     kind = K_EMIT; lflags |= LF_PARSE | LF_PREF | LF_JOB; flen = (uint32_t)(b - a) + 2u;
@@ -1396,6 +1506,9 @@ __device__ void process_window(const KParams &P, FSmem &S, uint32_t first_seg, u
         PROF(8);
         __syncthreads();
         PROF(4);
+        stage2_records(P, S, tot_j, rb);
+        __syncthreads();
+        #pragma unroll 1
         for (uint32_t i = w; i < min(S.jq_n, (uint32_t)JQ_CAP); i += F_WARPS) {      // unquote jobs: one warp per string
             const FJob jb = S.jq[i];
             if (jb.patch) warp_unquote2(S.tile, jb.s, jb.e, P.text + jb.dst, jb.patch);
@@ -1438,14 +1551,15 @@ __device__ void process_window(const KParams &P, FSmem &S, uint32_t first_seg, u
             }
         }
         // ---------------- serializer: lines whose bytes do not stand in the input as they must be sent
+        #pragma unroll 1
         for (uint32_t i = w; i < S.bc[9]; i += F_WARPS) {
             const FLine ln = S.line[S.matlist[i]];
             uint8_t *dst = P.out + ln.out_off;
-            if (!(ln.flags & LF_RMODE)) copy_s2g_vec(dst, S.tile + ln.start, (int)ln.nl + 1 - (int)ln.start);
-            else if ((ln.flags & LF_KIND) == K_DONE && !(ln.flags & LF_PREF)) copy_s2g_vec(dst, S.tile + ln.a, (int)ln.b - (int)ln.a);
+            if (!(ln.flags & LF_RMODE)) copy_s2g(dst, S.tile + ln.start, (int)ln.nl + 1 - (int)ln.start);
+            else if ((ln.flags & LF_KIND) == K_DONE && !(ln.flags & LF_PREF)) copy_s2g(dst, S.tile + ln.a, (int)ln.b - (int)ln.a);
             else {
                 const int body = (int)ln.b - (int)ln.a;        // "data: " + payload is contiguous in the tile
-                copy_s2g_vec(dst, S.tile + ln.a, body);
+                copy_s2g(dst, S.tile + ln.a, body);
                 if (lane < 2) dst[body + lane] = (uint8_t)'\n';
             }
         }
@@ -1499,7 +1613,7 @@ __device__ __noinline__ uint32_t tail_start(const FSmem &S, uint32_t lo, uint32_
 
 // Final state of a segment whose bytes have all been through a window: carry tail, connection state, result.
 // Called by a whole warp.
-__device__ void finish_segment(const KParams &P, FSmem &S, uint32_t first_seg, uint32_t i) {
+__device__ __noinline__ void finish_segment(const KParams &P, FSmem &S, uint32_t first_seg, uint32_t i) {
     const uint32_t lane = threadIdx.x & 31u;
     FSeg &sg = S.seg[i];
     const uint32_t gs = first_seg + i;
@@ -1518,7 +1632,7 @@ __device__ void finish_segment(const KParams &P, FSmem &S, uint32_t first_seg, u
             if (tl) {   // stored so that it ENDS at a 16-byte boundary of the slot: the next batch stages it with one aligned bulk copy
                 uint8_t *slot = P.carry + (size_t)sg.conn * P.carry_slot;
                 const uint32_t pad = (16u - (tl & 15u)) & 15u;
-                copy_s2g_vec(slot + pad, S.tile + ts, (int)tl);
+                copy_s2g(slot + pad, S.tile + ts, (int)tl);
             }
         }
     }
@@ -1536,6 +1650,62 @@ __device__ __forceinline__ void wait_tile(FSmem &S, uint32_t &phase, uint32_t to
     phase ^= 1u;
 }
 
+// A segment that does not fit a tile (carry + bytes): one CTA walks it window by window; a window starts at the line the
+// previous one left unterminated. (S.bc[4..7]: input offset, input end, carry length, connection.) Returns the barrier phase.
+__device__ __noinline__ uint32_t big_segment(const KParams &P, FSmem &S, uint32_t first, uint32_t phase) {
+    const uint32_t tid = threadIdx.x, w = tid >> 5;
+    uint32_t src = S.bc[4];
+    const uint32_t in_end = S.bc[5];
+    uint32_t cl = S.bc[6];
+    const uint32_t conn = S.bc[7];
+    uint32_t front = 0;                   // bytes of the first loaded vector that belong to an earlier line
+    for (;;) {
+        const uint32_t Aw = (cl + 15u) & ~15u;
+        const uint32_t room = TILE - Aw;
+        const uint32_t nbytes = min(in_end - src, room);
+        const uint32_t ldw = (nbytes + 15u) & ~15u;
+        const uint32_t tot = Aw + ldw;
+        if (tid == 0) {
+            FSeg &sg = S.seg[0];
+            sg.data_off = cl ? Aw - cl : front; sg.in_pos = Aw; sg.end = Aw + nbytes; sg.in_delta = src - Aw;
+        }
+        fence_proxy_async();
+        if (tid == 0) {
+            mbar_expect_tx(&S.mbar, tot);
+            if (Aw) bulk_g2s(S.tile, P.carry + (size_t)conn * P.carry_slot, Aw, &S.mbar);
+            if (ldw) bulk_g2s(S.tile + Aw, P.in + src, ldw, &S.mbar);
+        }
+        __syncthreads();
+        wait_tile(S, phase, tot);
+        if (tid == 0) {
+            const uint32_t d0 = cl ? Aw - cl : front;
+            for (uint32_t q = 0; q < d0; q++) S.tile[q] = 0;
+            if (!cl) for (uint32_t q = Aw; q < Aw + front; q++) S.tile[q] = 0;
+            for (uint32_t q = Aw + nbytes; q < tot; q++) S.tile[q] = 0;
+        }
+        __syncthreads();
+        process_window(P, S, first, 1, tot);
+        __syncthreads();
+        const uint32_t st = S.seg[0].state;
+        const bool last = src + nbytes >= in_end;
+        if ((st & (FS_TERM | FS_DEAD)) || last) break;
+        if (tid == 0) S.bc[8] = tail_start(S, S.seg[0].data_off, S.seg[0].end);
+        __syncthreads();
+        const uint32_t ts = S.bc[8];
+        if (ts == S.seg[0].data_off) {        // a whole window without '\n': the line is longer than carry_slot_bytes can be
+            if (tid == 0) S.seg[0].state |= FS_DEAD;
+            __syncthreads();
+            break;
+        }
+        const uint32_t X = ts + S.seg[0].in_delta;    // input offset of the unterminated line (ts >= in_pos here)
+        __syncthreads();
+        src = X & ~15u; front = X & 15u; cl = 0;
+    }
+    if (w == 0) finish_segment(P, S, first, 0);
+    __syncthreads();
+    return phase;
+}
+
 __global__ void __launch_bounds__(F_THREADS, 2)
 sse_fused_kernel(const __grid_constant__ KParams P, const FTables *__restrict__ gT) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -1547,13 +1717,13 @@ sse_fused_kernel(const __grid_constant__ KParams P, const FTables *__restrict__ 
         for (int i = tid; i < (int)(sizeof(FTables) / 4); i += F_THREADS) dst[i] = src[i];
     }
     if (tid == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); S.rec_busy = 0; S.build_lock = 0; }
-    if (tid < 256) S.thead[tid] = 0;
+    if (tid < W_STRUCT + 8) S.thead[tid] = 0;
     // the templates learnt by earlier launches (a cache: results never depend on what it holds)
     uint32_t t_loaded = 1;
     if (P.tcache) {
         t_loaded = min(max(P.tcache[0], 1u), (uint32_t)TS_WORDS);
         if (t_loaded > 1u) {
-            for (uint32_t i = tid; i < 256u; i += F_THREADS) S.thead[i] = P.tcache[1u + i];
+            for (uint32_t i = tid; i < (uint32_t)W_STRUCT + 8u; i += F_THREADS) S.thead[i] = P.tcache[1u + i];
             for (uint32_t i = tid; i < t_loaded; i += F_THREADS) S.tstore[i] = P.tcache[257u + i];
         }
     }
@@ -1634,60 +1804,10 @@ sse_fused_kernel(const __grid_constant__ KParams P, const FTables *__restrict__ 
         }
 
         // ---------------- a segment larger than the tile: windows, restarting at the unterminated line
-        {
-            __syncthreads();
-            uint32_t src = sd.in_off, in_end = sd.in_off + sd.in_len;     // (thread 0's values; broadcast below)
-            if (tid == 0) { S.bc[4] = src; S.bc[5] = in_end; S.bc[6] = clen; S.bc[7] = sd.conn; }
-            __syncthreads();
-            src = S.bc[4]; in_end = S.bc[5];
-            uint32_t cl = S.bc[6];
-            const uint32_t conn = S.bc[7];
-            uint32_t front = 0;                   // bytes of the first loaded vector that belong to an earlier line
-            for (;;) {
-                const uint32_t Aw = (cl + 15u) & ~15u;
-                const uint32_t room = TILE - Aw;
-                const uint32_t nbytes = min(in_end - src, room);
-                const uint32_t ldw = (nbytes + 15u) & ~15u;
-                const uint32_t tot = Aw + ldw;
-                if (tid == 0) {
-                    FSeg &sg = S.seg[0];
-                    sg.data_off = cl ? Aw - cl : front; sg.in_pos = Aw; sg.end = Aw + nbytes; sg.in_delta = src - Aw;
-                }
-                fence_proxy_async();
-                if (tid == 0) {
-                    mbar_expect_tx(&S.mbar, tot);
-                    if (Aw) bulk_g2s(S.tile, P.carry + (size_t)conn * P.carry_slot, Aw, &S.mbar);
-                    if (ldw) bulk_g2s(S.tile + Aw, P.in + src, ldw, &S.mbar);
-                }
-                __syncthreads();
-                wait_tile(S, phase, tot);
-                if (tid == 0) {
-                    const uint32_t d0 = cl ? Aw - cl : front;
-                    for (uint32_t q = 0; q < d0; q++) S.tile[q] = 0;
-                    if (!cl) for (uint32_t q = Aw; q < Aw + front; q++) S.tile[q] = 0;
-                    for (uint32_t q = Aw + nbytes; q < tot; q++) S.tile[q] = 0;
-                }
-                __syncthreads();
-                process_window(P, S, first, 1, tot);
-                __syncthreads();
-                const uint32_t st = S.seg[0].state;
-                const bool last = src + nbytes >= in_end;
-                if ((st & (FS_TERM | FS_DEAD)) || last) break;
-                if (tid == 0) S.bc[8] = tail_start(S, S.seg[0].data_off, S.seg[0].end);
-                __syncthreads();
-                const uint32_t ts = S.bc[8];
-                if (ts == S.seg[0].data_off) {        // a whole window without '\n': the line is longer than carry_slot_bytes can be
-                    if (tid == 0) S.seg[0].state |= FS_DEAD;
-                    __syncthreads();
-                    break;
-                }
-                const uint32_t X = ts + S.seg[0].in_delta;    // input offset of the unterminated line (ts >= in_pos here)
-                __syncthreads();
-                src = X & ~15u; front = X & 15u; cl = 0;
-            }
-            if (w == 0) finish_segment(P, S, first, 0);
-            __syncthreads();
-        }
+        __syncthreads();
+        if (tid == 0) { S.bc[4] = sd.in_off; S.bc[5] = sd.in_off + sd.in_len; S.bc[6] = clen; S.bc[7] = sd.conn; }
+        __syncthreads();
+        phase = big_segment(P, S, first, phase);
     }
     // one CTA hands what it has learnt to the next launch (all CTAs see the same kinds of lines)
     if (P.tcache && blockIdx.x == 0) {
@@ -1695,7 +1815,7 @@ sse_fused_kernel(const __grid_constant__ KParams P, const FTables *__restrict__ 
         const uint32_t used = min(S.ts_used, (uint32_t)TS_WORDS);
         if (used > t_loaded) {
             for (uint32_t i = tid; i < used; i += F_THREADS) P.tcache[257u + i] = S.tstore[i];
-            for (uint32_t i = tid; i < 256u; i += F_THREADS) P.tcache[1u + i] = S.thead[i];
+            for (uint32_t i = tid; i < (uint32_t)W_STRUCT + 8u; i += F_THREADS) P.tcache[1u + i] = S.thead[i];
             __threadfence();
             __syncthreads();
             if (tid == 0) P.tcache[0] = used;
@@ -1832,7 +1952,9 @@ int sse_launch_fused(const KParams &p, void *stream, int sm_count, int device) {
     sse_plan_kernel<<<(groups + 3) / 4, 128, 0, (cudaStream_t)stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    int grid = sm_count * 2;       // persistent: two resident CTAs per SM pull tiles by ticket
+    static int per_sm = 0;
+    if (!per_sm) { const char *e = getenv("SSE_CTAS_PER_SM"); per_sm = e ? atoi(e) : 2; if (per_sm < 1 || per_sm > 2) per_sm = 2; }
+    int grid = sm_count * per_sm;  // persistent: two resident CTAs per SM pull tiles by ticket
     sse_fused_kernel<<<grid, F_THREADS, sizeof(FSmem), (cudaStream_t)stream>>>(p, g_ftables_dev[device]);
     return (int)cudaGetLastError();
 }
