@@ -5,7 +5,7 @@ A step = one pass of the hot path over one micro-batch of synthetic SSE input: w
 (65,536 concurrent mixed cohere/groq/anthropic/ollama streams incl. tool_calls deltas, ~512 B mean chunk,
 mode R = MCP reframe + JSON side-band) per GPU, every stream complete in the batch (11 SSE events).
 
-  value      emitted chunks/s with the batch already resident in HBM (plan + fused kernel, CUDA events); the timed steps
+  value      emitted chunks/s with the batch already resident in HBM (all kernels of the step, CUDA events); the timed steps
              rotate over three resident copies of the input, so no step finds its input in L2
   segmented  the same streams cut into k seeded TCP pieces: a step is k launches, the unterminated tails travel through
              the per-connection carry slots (no reset between the pieces)
@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--streams", type=int, default=None, help="concurrent streams per GPU (default: the workload's)")
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", type=int, default=None, help="override the workload's mode bits (0 P, 2 P+parse, 3 R+parse)")
-    ap.add_argument("--flags", type=int, default=0, help="sse_config.flags (1 v1 kernel, 4 round-1 split pipeline, 8 copy-out, 16 no templates)")
+    ap.add_argument("--flags", type=int, default=0, help="sse_config.flags (4 single-pass tile kernel, 8 copy-out, 16 skeleton-template replay)")
     ap.add_argument("--segments", type=int, default=4, help="TCP pieces per stream of the segmented measurement (0: skip it)")
     ap.add_argument("--n-content", type=int, default=None, help="content deltas per stream (default: the config's 7)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -453,7 +453,9 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": "sse_fused_kernel (+ sse_plan_kernel, 2 launches per step; the whole step is timed)",
+                "kernel": ("sse_fused_kernel (+ sse_plan_kernel: 2 launches per step; the whole step is timed)" if args.flags & 4 else
+                           "sse_stream_kernel<produce> + sse_decode_kernel (+ bucket hist/scan/scatter and finalize: 6 launches per step; "
+                           "the whole step is timed)"),
                 "alg_bytes_per_launch": alg_bytes, "moved_bytes_per_launch": moved_bytes,
                 "zero_copy_frames": counts["zero_copy_frames"], "kernel_ms": 1e3 * kern_s,
                 "hbm_read_frac": counts["in_bytes"] / kern_s / 1e9 / peak}

@@ -42,7 +42,10 @@ typedef enum {
     SSE_ERR_ARG = -3,
     SSE_ERR_BUSY = -4,        /* no free batch slot / slot in wrong state */
     SSE_ERR_OVERFLOW = -5,    /* a result arena was too small for this batch (config too small) */
-    SSE_ERR_NOMEM = -6
+    SSE_ERR_NOMEM = -6,
+    SSE_ERR_UNDECODED = -7    /* sse_agent_feed / sse_telemetry_feed: the segment holds a record flagged SSE_F_TOO_LONG or SSE_F_DEPTH_LIMIT, i.e. a
+                                 line the reference would have decoded and this library did not: the fold took the rest, the caller must
+                                 fail the stream (or decode that frame itself) instead of trusting the accumulators */
 } sse_status;
 
 /* segment modes (per connection, chosen by which reference consumer sits above the provider) */
@@ -67,10 +70,10 @@ typedef struct {
     uint32_t flags;            /* SSE_FLAG_* */
 } sse_config;
 
-#define SSE_FLAG_KERNEL_V1 1u  /* fused first-generation kernel (sequential per-lane decoder) */
-#define SSE_FLAG_KERNEL_V2 2u  /* fused producer/consumer kernel (table-driven automaton); default is the split pipeline */
-#define SSE_FLAG_KERNEL_SPLIT 4u /* round-1 split pipeline (produce / sort / decode / finalize kernels) */
-#define SSE_FLAG_NO_TEMPLATES 16u /* fused kernel: every line through the JSON automaton (no skeleton-template replay) */
+#define SSE_FLAG_KERNEL_FUSED 4u /* single-pass tile kernel (1-D TMA staging, stop bitmap, warp-per-line template replay): reads the payload from HBM
+                                    once; slower than the default pipeline on B200 */
+#define SSE_FLAG_TEMPLATES 16u /* skeleton-template replay: lines whose JSON skeleton was seen before skip the automaton (results identical;
+                                  measured slower than the automaton alone on B200, DESIGN.md 4.4, so off by default) */
 #define SSE_FLAG_COPY_OUT 8u   /* materialise every frame in the out arena. Default: a frame whose bytes already stand in the
                                   caller's input arena exactly as the reference would send them (every mode P line, and a mode R
                                   "data: ...\n" line followed by a blank line) is returned as a span of the input arena and is
@@ -248,6 +251,10 @@ sse_telemetry_fold *sse_telemetry_new(void);
 void sse_telemetry_free(sse_telemetry_fold *f);
 void sse_telemetry_reset(sse_telemetry_fold *f);
 int  sse_telemetry_feed(sse_telemetry_fold *f, const sse_result *res, uint32_t seg_index);
+/* Bytes the HOST writes to the client between upstream frames: ssegw_agent_recv's final "data: [DONE]\n\n" (agent.go:140-143).
+ * They are part of the body telemetry.go:190-198 splits into pieces, so they move its last-4-pieces window; they are not decoded
+ * (feed only frames that hold no chunk: "[DONE]", comments, error text). n must end on a '\n'. */
+int  sse_telemetry_feed_bytes(sse_telemetry_fold *f, const uint8_t *bytes, size_t n);
 int  sse_telemetry_finish(sse_telemetry_fold *f, sse_usage *usage, sse_tool_call *calls, size_t cap, size_t *n_calls);
 
 #ifdef __cplusplus

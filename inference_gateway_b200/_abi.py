@@ -6,9 +6,9 @@ import os
 
 from . import build as _build
 
-SSE_OK, SSE_ERR_NO_DEVICE, SSE_ERR_CUDA, SSE_ERR_ARG, SSE_ERR_BUSY, SSE_ERR_OVERFLOW, SSE_ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
+SSE_OK, SSE_ERR_NO_DEVICE, SSE_ERR_CUDA, SSE_ERR_ARG, SSE_ERR_BUSY, SSE_ERR_OVERFLOW, SSE_ERR_NOMEM, SSE_ERR_UNDECODED = 0, -1, -2, -3, -4, -5, -6, -7
 MODE_P, MODE_R, MODE_PARSE = 0, 1, 2
-FLAG_KERNEL_V1, FLAG_KERNEL_V2, FLAG_COPY_OUT = 1, 2, 8
+FLAG_KERNEL_FUSED, FLAG_COPY_OUT, FLAG_TEMPLATES = 4, 8, 16
 NONE = 0xFFFFFFFF
 
 F_JSON_OK, F_HAS_USAGE, F_TC_NONNIL, F_TC_VALID, F_CONTENT_TEXT = 0x1, 0x2, 0x4, 0x8, 0x10
@@ -91,7 +91,7 @@ EXPORTS = [
     "sse_upload", "sse_launch", "sse_download", "sse_launch_count", "sse_at",
     "sse_agent_new", "sse_agent_free", "sse_agent_reset", "sse_agent_feed", "sse_agent_content",
     "sse_agent_has_tool_calls", "sse_agent_terminated", "sse_agent_tool_calls",
-    "sse_telemetry_new", "sse_telemetry_free", "sse_telemetry_reset", "sse_telemetry_feed", "sse_telemetry_finish",
+    "sse_telemetry_new", "sse_telemetry_free", "sse_telemetry_reset", "sse_telemetry_feed", "sse_telemetry_feed_bytes", "sse_telemetry_finish",
 ]
 
 _lib = None
@@ -121,6 +121,8 @@ def load(build_if_missing: bool = True):
     L.sse_last_cuda_error.restype = C.c_char_p
     L.sse_default_config.argtypes = [C.POINTER(Config), u32, u32]
     L.sse_default_config.restype = None
+    L.sse_worst_case_config.argtypes = [C.POINTER(Config), u32, u32]
+    L.sse_worst_case_config.restype = None
     L.sse_acquire.argtypes = [vp, C.POINTER(i32), C.POINTER(Batch)]
     L.sse_submit.argtypes = [vp, i32, u32, u32]
     L.sse_collect.argtypes = [vp, i32, C.POINTER(Result)]
@@ -154,6 +156,7 @@ def load(build_if_missing: bool = True):
     L.sse_telemetry_reset.argtypes = [vp]
     L.sse_telemetry_reset.restype = None
     L.sse_telemetry_feed.argtypes = [vp, C.POINTER(Result), u32]
+    L.sse_telemetry_feed_bytes.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.sse_telemetry_finish.argtypes = [vp, C.POINTER(Usage), C.POINTER(ToolCall), C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = L
     return L

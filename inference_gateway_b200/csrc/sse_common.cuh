@@ -192,59 +192,6 @@ __device__ __forceinline__ int hex4(const uint8_t *s) {
     if ((a | b | c | d) < 0) return -1;
     return (a << 12) | (b << 8) | (c << 4) | d;
 }
-// Scan a string literal; p at the opening quote. Returns the position after the closing quote or -1.
-// esc: a backslash was seen; bad: invalid UTF-8 was seen (Go replaces it with U+FFFD when unquoting).
-__device__ __noinline__ int scan_string(const uint8_t *sm, int p, int pe, bool &esc, bool &bad) {
-    p++;
-    while (p < pe) {
-        uint32_t c = sm[p];
-        if (c == '"') return p + 1;
-        if (c < 0x20) return -1;
-        if (c == '\\') {
-            esc = true;
-            if (p + 1 >= pe) return -1;
-            uint32_t e = sm[p + 1];
-            if (e == 'u') {
-                if (p + 6 > pe || hex4(sm + p + 2) < 0) return -1;
-                p += 6;
-            } else if (e == '"' || e == '\\' || e == '/' || e == 'b' || e == 'f' || e == 'n' || e == 'r' || e == 't') {
-                p += 2;
-            } else return -1;
-            continue;
-        }
-        if (c >= 0x80) {
-            int k = utf8_valid_len(sm + p, pe - p);
-            if (k == 0) { bad = true; p++; } else p += k;
-            continue;
-        }
-        p++;
-    }
-    return -1;
-}
-// Scan a number literal. Returns end or -1. is_int: no fraction / exponent.
-__device__ __noinline__ int scan_number(const uint8_t *sm, int p, int pe, bool &is_int) {
-    is_int = true;
-    if (p < pe && sm[p] == '-') p++;
-    if (p >= pe) return -1;
-    uint32_t c = sm[p];
-    if (c == '0') p++;
-    else if (c >= '1' && c <= '9') { while (p < pe && (uint32_t)(sm[p] - '0') <= 9u) p++; }
-    else return -1;
-    if (p < pe && sm[p] == '.') {
-        is_int = false;
-        p++;
-        if (p >= pe || (uint32_t)(sm[p] - '0') > 9u) return -1;
-        while (p < pe && (uint32_t)(sm[p] - '0') <= 9u) p++;
-    }
-    if (p < pe && (sm[p] == 'e' || sm[p] == 'E')) {
-        is_int = false;
-        p++;
-        if (p < pe && (sm[p] == '+' || sm[p] == '-')) p++;
-        if (p >= pe || (uint32_t)(sm[p] - '0') > 9u) return -1;
-        while (p < pe && (uint32_t)(sm[p] - '0') <= 9u) p++;
-    }
-    return p;
-}
 // strconv.ParseInt(s, 10, 64) on an integer literal [s, e)
 __device__ __noinline__ bool parse_i64(const uint8_t *sm, int s, int e, int64_t &out) {
     bool neg = false;
@@ -529,267 +476,11 @@ __device__ __noinline__ void warp_unquote(const uint8_t *__restrict__ src, uint3
     __syncwarp();
 }
 
-struct PendingTc {
-    int64_t index;
-    uint32_t flags;            // SSE_TC_HAS_*
-    uint32_t id, type, name, args;   // packed (s << 16) | e window spans
-    uint32_t dec;              // bit0 id, bit1 type, bit2 name, bit3 args need unquoting
-};
-
 struct ParseOut {
     uint32_t flags;
     uint32_t content_off, content_len;
     uint32_t tc_first, tc_count, n_choices, usage;
 };
-
-__device__ __noinline__ void flush_tc(const ParseCtx &cx, PendingTc &t, uint32_t &tc_first, uint32_t &tc_prev, bool &tc_valid) {
-    auto cap = [&](uint32_t sp, bool dec) { return capture(cx, (int)(sp >> 16), (int)(sp & 0xFFFF), dec ? 3 : 0); };
-    Span id = cap(t.id, t.dec & 1), ty = cap(t.type, t.dec & 2), nm = cap(t.name, t.dec & 4), ar = cap(t.args, t.dec & 8);
-    if ((t.flags & SSE_TC_HAS_ID) || ((t.flags & SSE_TC_HAS_FUNC) && (nm.len || ar.len))) tc_valid = true;
-    uint32_t idx = atomicAdd(&cx.P->ctr->n_tcs, 1u);
-    if (idx >= cx.P->cap_tcs) { sse_overflow(cx.P->ctr, SSE_OVF_TCS); return; }
-    sse_tc o;
-    o.index = t.index;
-    o.flags = t.flags | (id.text ? SSE_TC_ID_TEXT : 0) | (ty.text ? SSE_TC_TYPE_TEXT : 0) |
-              (nm.text ? SSE_TC_NAME_TEXT : 0) | (ar.text ? SSE_TC_ARGS_TEXT : 0);
-    o.next = SSE_NONE;
-    o.id_off = id.off; o.id_len = id.len; o.type_off = ty.off; o.type_len = ty.len;
-    o.name_off = nm.off; o.name_len = nm.len; o.args_off = ar.off; o.args_len = ar.len;
-    cx.P->tcs[idx] = o;
-    if (tc_first == SSE_NONE) tc_first = idx; else cx.P->tcs[tc_prev].next = idx;
-    tc_prev = idx;
-}
-
-enum : int { ST_VALUE, ST_OBJ_FIRST, ST_OBJ_KEY, ST_COLON, ST_AFTER, ST_ARR_FIRST, ST_END };
-
-// json.Unmarshal(payload, &CreateChatCompletionStreamResponse) + the reads of agent.go:205-242.
-// Single pass: syntax (scanner.go), type compatibility (decode.go literalStore/object/array) and extraction.
-__device__ __noinline__ void decode_chunk(const ParseCtx &cx, int p, int pe, ParseOut &out) {
-    const uint8_t *sm = cx.sm;
-    const Schema &S = *cx.S;
-    int state = ST_VALUE, depth = 0, skip = 0, sd = 0;
-    unsigned long long ct0 = 0, ct1 = 0, sstk = 0;
-    bool syn = false, type_err = false, depth_limit = false, google_bad = false;
-    uint32_t cur_ty = TY_ROOT, cur_sub = N_ROOT, cur_tgt = TG_NONE;
-    uint32_t choices_count = 0, n_choices = 0;
-    bool has_usage = false;
-    int64_t u_prompt = 0, u_completion = 0, u_total = 0;
-    uint32_t finish = SSE_FIN_NONE;
-    uint32_t content_sp = 0; bool content_dec = false;
-    bool tc_nonnil = false, tc_open = false, tc_valid = false;
-    uint32_t tc_count = 0, tc_first = SSE_NONE, tc_prev = SSE_NONE;
-    PendingTc tc; tc.index = 0; tc.flags = 0; tc.id = tc.type = tc.name = tc.args = 0; tc.dec = 0;
-
-#define LIVE() (sd >= 3 && ((sstk >> 10) & 31ull) == N_CHOICE && choices_count == 1)
-#define TOPNODE() ((uint32_t)((sstk >> (5 * (sd - 1))) & 31ull))
-#define FLUSH_TC() do { if (tc_open) { flush_tc(cx, tc, tc_first, tc_prev, tc_valid); tc_open = false; } } while (0)
-#define ELEM_BEGIN() do { \
-        if (skip > 0) { cur_ty = TY_SKIP; cur_tgt = TG_NONE; } \
-        else { \
-            uint32_t nd_ = TOPNODE(); cur_tgt = TG_NONE; \
-            if (nd_ == A_CHOICES) { choices_count++; cur_ty = TY_STRUCT; cur_sub = N_CHOICE; } \
-            else if (nd_ == A_TOOLCALLS) { \
-                cur_ty = TY_STRUCT; cur_sub = N_TC; \
-                if (LIVE()) { FLUSH_TC(); tc_open = true; tc_count++; tc.index = 0; tc.flags = 0; tc.id = tc.type = tc.name = tc.args = 0; tc.dec = 0; } \
-            } \
-            else if (nd_ == A_TOKLP) { cur_ty = TY_STRUCT; cur_sub = N_TOKLP; } \
-            else if (nd_ == A_TOPLP) { cur_ty = TY_STRUCT; cur_sub = N_TOPLP; } \
-            else { cur_ty = TY_INT; } \
-        } } while (0)
-
-    for (;;) {
-        while (p < pe) { uint32_t w = sm[p]; if (w == ' ' || w == '\t' || w == '\r' || w == '\n') p++; else break; }
-        if (p >= pe) { if (state != ST_END) syn = true; break; }
-        uint32_t c = sm[p];
-        bool do_value = false, do_close = false;
-        switch (state) {
-        case ST_END: syn = true; break;
-        case ST_COLON:
-            if (c != ':') { syn = true; break; }
-            p++; state = ST_VALUE; break;
-        case ST_OBJ_FIRST:
-            if (c == '}') { p++; do_close = true; break; }
-            /* fallthrough */
-        case ST_OBJ_KEY: {
-            if (c != '"') { syn = true; break; }
-            bool esc = false, bad = false;
-            int q = scan_string(sm, p, pe, esc, bad);
-            if (q < 0) { syn = true; break; }
-            cur_ty = TY_SKIP; cur_tgt = TG_NONE; cur_sub = N_NONE;
-            if (skip == 0) {
-                int node = (int)TOPNODE();
-                int ks = p + 1, ke = q - 1, f;
-                if (!esc && !bad) f = match_field(S, node, sm + ks, ke - ks);
-                else {
-                    uint8_t tmp[72];
-                    uint32_t n = json_unquote(sm, ks, ke, tmp, 64);
-                    f = (n <= 64) ? match_field(S, node, tmp, (int)n) : -1;
-                }
-                if (f >= 0) { cur_ty = S.f[f].ty; cur_sub = S.f[f].sub; cur_tgt = S.f[f].tgt; }
-            }
-            p = q; state = ST_COLON; break;
-        }
-        case ST_ARR_FIRST:
-            if (c == ']') { p++; do_close = true; break; }
-            ELEM_BEGIN();
-            do_value = true; break;
-        case ST_VALUE: do_value = true; break;
-        case ST_AFTER: {
-            bool is_arr = (depth <= 64) ? ((ct0 >> (depth - 1)) & 1ull) : ((ct1 >> (depth - 65)) & 1ull);
-            if (c == ',') {
-                p++;
-                if (is_arr) { ELEM_BEGIN(); state = ST_VALUE; } else state = ST_OBJ_KEY;
-            } else if (c == (is_arr ? (uint32_t)']' : (uint32_t)'}')) { p++; do_close = true; }
-            else syn = true;
-            break;
-        }
-        }
-        if (syn) break;
-        if (do_close) {
-            depth--;
-            if (skip > 0) skip--;
-            else {
-                uint32_t node = TOPNODE();
-                sd--;
-                if (node == A_CHOICES) n_choices = choices_count;
-                else if (node == A_TOOLCALLS) { if (LIVE()) FLUSH_TC(); }
-                else if (node == N_GOOGLE) { if (google_bad) type_err = true; }
-            }
-            state = depth == 0 ? ST_END : ST_AFTER;
-            continue;
-        }
-        if (!do_value) continue;
-        // ---- a value starts at p
-        if (c == '{' || c == '[') {
-            bool arr = c == '[';
-            if (depth >= 128) { depth_limit = true; syn = true; break; }
-            if (depth < 64) ct0 = (ct0 & ~(1ull << depth)) | ((unsigned long long)arr << depth);
-            else ct1 = (ct1 & ~(1ull << (depth - 64))) | ((unsigned long long)arr << (depth - 64));
-            depth++; p++;
-            if (skip > 0 || cur_ty == TY_SKIP) skip++;
-            else {
-                bool ok = arr ? (cur_ty == TY_SLICE || cur_ty == TY_PSLICE)
-                              : (cur_ty == TY_STRUCT || cur_ty == TY_PSTRUCT || cur_ty == TY_ROOT || cur_ty == TY_GOOGLE);
-                if (!ok) { if (cur_ty == TY_TS) google_bad = true; else type_err = true; skip++; }
-                else {
-                    bool live = LIVE();
-                    sstk = (sstk & ~(31ull << (5 * sd))) | ((unsigned long long)cur_sub << (5 * sd));
-                    sd++;
-                    if (cur_tgt == TG_USAGE) has_usage = true;
-                    else if (cur_tgt == TG_TC_FUNCTION) { if (live && tc_open) tc.flags |= SSE_TC_HAS_FUNC; }
-                    else if (cur_tgt == TG_CHOICES) choices_count = 0;
-                    else if (cur_tgt == TG_TOOLCALLS) {
-                        if (live) { tc_nonnil = true; tc_count = 0; tc_first = SSE_NONE; tc_prev = SSE_NONE; tc_open = false; tc_valid = false; }
-                    }
-                    if (cur_sub == N_GOOGLE) google_bad = false;
-                }
-            }
-            state = arr ? ST_ARR_FIRST : ST_OBJ_FIRST;
-            continue;
-        }
-        if (c == '"') {
-            bool esc = false, bad = false;
-            int q = scan_string(sm, p, pe, esc, bad);
-            if (q < 0) { syn = true; break; }
-            if (cur_ty == TY_STR || cur_ty == TY_PSTR) {
-                if (cur_tgt != TG_NONE && LIVE()) {
-                    uint32_t sp = ((uint32_t)(p + 1) << 16) | (uint32_t)(q - 1);
-                    bool dec = esc || bad;
-                    switch (cur_tgt) {
-                    case TG_CONTENT: content_sp = sp; content_dec = dec; break;
-                    case TG_FINISH:
-                        if (!dec) finish = classify_finish(sm + p + 1, q - p - 2);
-                        else {
-                            uint8_t tmp[40];
-                            uint32_t n = json_unquote(sm, p + 1, q - 1, tmp, 32);
-                            finish = (n <= 32) ? classify_finish(tmp, (int)n) : (uint32_t)SSE_FIN_OTHER;
-                        }
-                        break;
-                    case TG_TC_ID: if (tc_open) { tc.flags |= SSE_TC_HAS_ID; tc.id = sp; tc.dec = (tc.dec & ~1u) | (dec ? 1u : 0u); } break;
-                    case TG_TC_TYPE: if (tc_open) { tc.flags |= SSE_TC_HAS_TYPE; tc.type = sp; tc.dec = (tc.dec & ~2u) | (dec ? 2u : 0u); } break;
-                    case TG_NAME: if (tc_open) { tc.name = sp; tc.dec = (tc.dec & ~4u) | (dec ? 4u : 0u); } break;
-                    case TG_ARGS: if (tc_open) { tc.args = sp; tc.dec = (tc.dec & ~8u) | (dec ? 8u : 0u); } break;
-                    default: break;
-                    }
-                }
-            } else if (cur_ty == TY_TS) google_bad = false;
-            else if (cur_ty != TY_SKIP) type_err = true;
-            p = q;
-        } else if (c == '-' || (c >= '0' && c <= '9')) {
-            bool is_int;
-            int q = scan_number(sm, p, pe, is_int);
-            if (q < 0) { syn = true; break; }
-            if (cur_ty == TY_INT) {
-                int64_t v;
-                if (!is_int || !parse_i64(sm, p, q, v)) type_err = true;
-                else if (cur_tgt == TG_PROMPT) u_prompt = v;
-                else if (cur_tgt == TG_COMPLETION) u_completion = v;
-                else if (cur_tgt == TG_TOTAL) u_total = v;
-                else if (cur_tgt == TG_TC_INDEX) { if (tc_open && LIVE()) tc.index = v; }
-            } else if (cur_ty == TY_F32) { if (f32_overflows(sm, p, q)) type_err = true; }
-            else if (cur_ty == TY_TS) google_bad = true;
-            else if (cur_ty != TY_SKIP) type_err = true;
-            p = q;
-        } else if (c == 't') {
-            if (p + 4 > pe || sm[p + 1] != 'r' || sm[p + 2] != 'u' || sm[p + 3] != 'e') { syn = true; break; }
-            p += 4;
-            if (cur_ty == TY_TS) google_bad = true; else if (cur_ty != TY_SKIP) type_err = true;
-        } else if (c == 'f') {
-            if (p + 5 > pe || sm[p + 1] != 'a' || sm[p + 2] != 'l' || sm[p + 3] != 's' || sm[p + 4] != 'e') { syn = true; break; }
-            p += 5;
-            if (cur_ty == TY_TS) google_bad = true; else if (cur_ty != TY_SKIP) type_err = true;
-        } else if (c == 'n') {
-            if (p + 4 > pe || sm[p + 1] != 'u' || sm[p + 2] != 'l' || sm[p + 3] != 'l') { syn = true; break; }
-            p += 4;
-            // literalStore(null): pointers / slices -> nil, everything else untouched
-            if (cur_ty == TY_TS) google_bad = false;
-            else switch (cur_tgt) {
-            case TG_CHOICES:
-                n_choices = 0; choices_count = 0; finish = SSE_FIN_NONE; content_sp = 0; content_dec = false;
-                tc_nonnil = false; tc_open = false; tc_valid = false; tc_count = 0; tc_first = SSE_NONE; tc_prev = SSE_NONE;
-                break;
-            case TG_USAGE: has_usage = false; u_prompt = u_completion = u_total = 0; break;
-            case TG_TOOLCALLS:
-                if (LIVE()) { tc_nonnil = false; tc_open = false; tc_valid = false; tc_count = 0; tc_first = SSE_NONE; tc_prev = SSE_NONE; }
-                break;
-            case TG_TC_ID: if (tc_open && LIVE()) { tc.flags &= ~SSE_TC_HAS_ID; tc.id = 0; tc.dec &= ~1u; } break;
-            case TG_TC_TYPE: if (tc_open && LIVE()) { tc.flags &= ~SSE_TC_HAS_TYPE; tc.type = 0; tc.dec &= ~2u; } break;
-            case TG_TC_FUNCTION: if (tc_open && LIVE()) { tc.flags &= ~SSE_TC_HAS_FUNC; tc.name = tc.args = 0; tc.dec &= ~12u; } break;
-            default: break;
-            }
-        } else { syn = true; break; }
-        state = depth == 0 ? ST_END : ST_AFTER;
-    }
-#undef LIVE
-#undef TOPNODE
-#undef FLUSH_TC
-#undef ELEM_BEGIN
-
-    out.flags = 0; out.content_off = 0; out.content_len = 0;
-    out.tc_first = SSE_NONE; out.tc_count = 0; out.n_choices = 0; out.usage = SSE_NONE;
-    if (depth_limit) out.flags |= SSE_F_DEPTH_LIMIT;
-    if (syn || type_err) return;
-    out.flags |= SSE_F_JSON_OK;
-    out.n_choices = n_choices;
-    if (has_usage) {
-        uint32_t idx = atomicAdd(&cx.P->ctr->n_usages, 1u);
-        if (idx < cx.P->cap_usages) {
-            sse_usage u; u.prompt_tokens = u_prompt; u.completion_tokens = u_completion; u.total_tokens = u_total;
-            cx.P->usages[idx] = u;
-            out.usage = idx; out.flags |= SSE_F_HAS_USAGE;
-        } else sse_overflow(cx.P->ctr, SSE_OVF_USAGES);
-    }
-    if (n_choices > 0) {
-        Span ct = capture(cx, (int)(content_sp >> 16), (int)(content_sp & 0xFFFF), content_dec ? 3 : 0);
-        out.content_off = ct.len ? ct.off : 0; out.content_len = ct.len;
-        if (ct.text && ct.len) out.flags |= SSE_F_CONTENT_TEXT;
-        out.flags |= finish << SSE_F_FINISH_SHIFT;
-        if (tc_nonnil) out.flags |= SSE_F_TC_NONNIL;
-        if (tc_valid) out.flags |= SSE_F_TC_VALID;
-        out.tc_first = tc_count ? tc_first : SSE_NONE;
-        out.tc_count = tc_count;
-    }
-}
 
 // ---------------------------------------------------------------- warp-cooperative helpers
 // copy n bytes global -> shared so that they END at smem offset `end_off` (byte granularity)
@@ -853,33 +544,44 @@ __device__ __noinline__ void append_run(const KParams &P, RunChain &rc, uint32_t
     rc.last_idx = idx;
 }
 
-// A line that never fit the window, assembled in the connection's carry slot (HBM): classified and emitted
-// straight from global memory; its payload is not decoded (SSE_F_TOO_LONG).
-__device__ __noinline__ bool process_long_line(const KParams &P, RunChain &rc, const uint8_t *line, int L, uint32_t mode) {
+// A line that never fit the window, assembled in the connection's carry slot (HBM): classified and emitted straight from
+// global memory. seg >= 0 (split pipeline): its payload becomes a work item like any other line's -- the decode kernel
+// reads payloads from the arenas, so a line of any length up to carry_slot_bytes is decoded. seg < 0 (first-generation
+// kernel): the payload is not decoded (SSE_F_TOO_LONG).
+__device__ __noinline__ bool process_long_line(const KParams &P, RunChain &rc, const uint8_t *line, int L, uint32_t mode, int seg = -1) {
     const uint32_t lane = lane_id();
     int a = 0, b = L;           // frame source [a, b) ; R: trimmed
-    bool emit = true, done = false, parse = false;
+    bool emit = true, done = false, parse = false, pref = false;
     int flen = L;
     if (mode & SSE_MODE_R) {
         trim_space(line, a, b);   // every lane, from global (ends only)
         bool found = false;
         for (int i = a + (int)lane; i + 6 <= b; i += 32) if (is_done_at(line + i)) found = true;
         done = __any_sync(FULL, found);
-        bool pref = is_data_prefix(line + a, b - a);
+        pref = is_data_prefix(line + a, b - a);
         emit = !done && pref && (b - a) > 6;
         flen = emit ? (b - a) + 2 : 0;
         parse = emit || (done);
     } else {
-        parse = (mode & SSE_MODE_PARSE) && is_data_prefix(line, L);
+        pref = is_data_prefix(line, L);
+        parse = (mode & SSE_MODE_PARSE) && pref;
     }
+    // payload handed to the decoder: [ps, pe) of the line
+    const int ps = (mode & SSE_MODE_R) ? (pref ? a + 6 : a) : 6, pe = (mode & SSE_MODE_R) ? b : L - 1;
+    const bool item = seg >= 0 && parse;
+    const bool exact = item && done && pref && pe - ps == 6;          // `data: [DONE]` cannot be this long; kept for symmetry
+    const uint32_t extra = (item && !emit) ? (uint32_t)(pe - ps) : 0u;   // a swallowed line's payload is materialised for the decoder
     uint32_t nf = emit ? 1u : 0u, nr = parse ? 1u : 0u;
-    uint32_t ob = 0, fb = 0, rb = 0;
+    uint32_t ob = 0, fb = 0, rb = 0, qb = 0;
     if (lane == 0) {
-        if (nf) { ob = atomicAdd(&P.ctr->out_bytes, (uint32_t)flen); fb = atomicAdd(&P.ctr->n_frames, 1u); }
+        if (nf || extra) ob = atomicAdd(&P.ctr->out_bytes, ((uint32_t)flen + extra + 15u) & ~15u);
+        if (nf) fb = atomicAdd(&P.ctr->n_frames, 1u);
         if (nr) rb = atomicAdd(&P.ctr->n_recs, 1u);
+        if (item && !exact) qb = atomicAdd(&P.ctr->n_items, 1u);
     }
-    ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0);
-    bool ovf = (nf && (ob + (uint32_t)flen > P.cap_out || fb >= P.cap_frames)) || (nr && rb >= P.cap_recs);
+    ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0); qb = __shfl_sync(FULL, qb, 0);
+    bool ovf = ((nf || extra) && (ob + (uint32_t)flen + extra + 16u > P.cap_out)) || (nf && fb >= P.cap_frames) || (nr && rb >= P.cap_recs) ||
+               (item && !exact && qb >= P.cap_items);
     if (ovf) { if (lane == 0) sse_overflow(P.ctr, SSE_OVF_OUT); return false; }
     if (emit) {
         if (mode & SSE_MODE_R) {
@@ -887,14 +589,21 @@ __device__ __noinline__ bool process_long_line(const KParams &P, RunChain &rc, c
             if (lane < 2) P.out[ob + (uint32_t)(b - a) + lane] = '\n';
         } else copy_g2g_bytes(P.out + ob, line, L);
         if (lane == 0) { sse_frame f; f.off = ob; f.len = (uint32_t)flen; P.frames[fb] = f; }
-    }
+    } else if (extra) copy_g2g_bytes(P.out + ob, line + ps, pe - ps);
     if (parse && lane == 0) {
         sse_rec r;
         r.frame = emit ? fb : SSE_NONE;
-        r.flags = SSE_F_TOO_LONG | (done ? SSE_F_DONE_LINE : 0u);
+        r.flags = item ? (exact ? (SSE_F_DONE_LINE | SSE_F_DONE_EXACT) : 0u) : (SSE_F_TOO_LONG | (done ? SSE_F_DONE_LINE : 0u));
         r.content_off = r.content_len = 0; r.tc_first = SSE_NONE; r.tc_count = 0; r.n_choices = 0; r.usage = SSE_NONE;
-        r.payload_len = (uint32_t)((mode & SSE_MODE_R) ? (b - a) : L);
+        r.payload_len = (uint32_t)(pe - ps);
         P.recs[rb] = r;
+        if (item && !exact) {
+            uint4 it;
+            it.x = emit ? ob + (uint32_t)(ps - ((mode & SSE_MODE_R) ? a : 0)) : ob;
+            it.y = (uint32_t)(pe - ps) | (done ? 0x40000000u : ((mode & SSE_MODE_R) ? 0x80000000u : 0u));
+            it.z = rb; it.w = (uint32_t)seg;
+            P.items[qb] = it;
+        }
     }
     append_run(P, rc, fb, nf, rb, nr);
     return true;

@@ -83,11 +83,9 @@ __device__ __forceinline__ void sse_overflow(Counters *c, uint32_t which) {
 #endif
 
 // launch wrappers (sse_kernel.cu)
-int sse_launch_stream_kernel(const KParams &p, void *stream, int sm_count);            // v1: per-lane sequential decoder
 int sse_launch_produce_kernel(const KParams &p, void *stream, int sm_count);           // split pipeline, stage 1
 int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int device);  // split pipeline, stages 2+3
 int sse_v2_prepare(int device);                                                        // builds + uploads the automaton tables
-int sse_launch_stream_kernel_v2(const KParams &p, void *stream, int sm_count, int device);
 int sse_fused_prepare(int device);                                                     // fused pipeline: tables + kernel attributes
 int sse_launch_fused(const KParams &p, void *stream, int sm_count, int device);        // plan kernel + fused tile kernel
 uint32_t sse_fused_max_line(void);

@@ -169,9 +169,11 @@ void sse_agent_reset(sse_agent_fold *f) { *f = sse_agent_fold(); }
 
 int sse_agent_feed(sse_agent_fold *f, const sse_result *res, uint32_t seg) {
     if (!f || !res || seg >= res->n_segs) return SSE_ERR_ARG;
+    bool undecoded = false;
     for_each_run(res, seg, [&](const sse_run &run) {
         for (uint32_t i = 0; i < run.rec_count; i++) {
             const sse_rec &r = res->recs[run.rec_first + i];
+            if (r.flags & (SSE_F_TOO_LONG | SSE_F_DEPTH_LIMIT)) undecoded = true;     // the reference would have decoded this line
             const bool done_line = (r.flags & SSE_F_DONE_LINE) != 0;
             const bool ok = (r.flags & SSE_F_JSON_OK) != 0;
             if (!done_line && ok && r.n_choices > 0) {                         // agent.go:205-242
@@ -218,7 +220,7 @@ int sse_agent_feed(sse_agent_fold *f, const sse_result *res, uint32_t seg) {
             }
         }
     });
-    return SSE_OK;
+    return undecoded ? SSE_ERR_UNDECODED : SSE_OK;
 }
 
 sse_bytes sse_agent_content(const sse_agent_fold *f) { return { (const uint8_t *)f->content.data(), f->content.size() }; }
@@ -234,7 +236,10 @@ void sse_telemetry_reset(sse_telemetry_fold *f) { *f = sse_telemetry_fold(); }
 
 int sse_telemetry_feed(sse_telemetry_fold *f, const sse_result *res, uint32_t seg) {
     if (!f || !res || seg >= res->n_segs) return SSE_ERR_ARG;
+    bool undecoded = false;
     for_each_run(res, seg, [&](const sse_run &run) {
+        for (uint32_t i = 0; i < run.rec_count; i++)
+            if (res->recs[run.rec_first + i].flags & (SSE_F_TOO_LONG | SSE_F_DEPTH_LIMIT)) undecoded = true;
         // records of this run in frame order: rec.frame is increasing
         uint32_t ri = 0;
         for (uint32_t i = 0; i < run.frame_count; i++) {
@@ -251,6 +256,14 @@ int sse_telemetry_feed(sse_telemetry_fold *f, const sse_result *res, uint32_t se
             } else tele_line(f, res, fr.len, rec);
         }
     });
+    return undecoded ? SSE_ERR_UNDECODED : SSE_OK;
+}
+
+int sse_telemetry_feed_bytes(sse_telemetry_fold *f, const uint8_t *bytes, size_t n) {
+    if (!f || (!bytes && n) || (n && bytes[n - 1] != '\n')) return SSE_ERR_ARG;
+    size_t s0 = 0;
+    for (size_t i = 0; i < n; i++)
+        if (bytes[i] == '\n') { tele_line(f, nullptr, (uint32_t)(i + 1 - s0), nullptr); s0 = i + 1; }   // no record: a piece that is not a chunk
     return SSE_OK;
 }
 

@@ -1321,7 +1321,7 @@ __device__ __noinline__ void stage2_automaton(const KParams &P, FSmem &S, bool h
     L.tcb = 0; L.usage_idx = SSE_NONE;
     if (has) {
         lane_setup(P, S, L, j, rb);
-        if (!(P.flags & SSE_FLAG_NO_TEMPLATES) && !(L.sf & SF_DONELINE) && S.ts_used + 360u <= (uint32_t)TS_WORDS) {
+        if ((P.flags & SSE_FLAG_TEMPLATES) && !(L.sf & SF_DONELINE) && S.ts_used + 360u <= (uint32_t)TS_WORDS) {
             uint32_t m = S.rec_busy;                 // record a template while the automaton walks the line
             while ((~m) & ((1u << NREC) - 1u)) {
                 const uint32_t b = (uint32_t)__ffs((~m) & ((1u << NREC) - 1u)) - 1u;
@@ -1348,7 +1348,7 @@ __device__ void stage2(const KParams &P, FSmem &S, uint32_t n_jobs, uint32_t rb)
     #pragma unroll 1
     for (uint32_t j = wid; j < n_jobs; j += F_WARPS) {
         bool hit = false;
-        if (!(P.flags & SSE_FLAG_NO_TEMPLATES)) hit = warp_replay(P, S, j, rb);
+        if ((P.flags & SSE_FLAG_TEMPLATES)) hit = warp_replay(P, S, j, rb);
         if (!hit && lane == 0) { PCOUNT(50, 1); FRes z; z.cpos = z.clen = z.toff = 0; z.misc = 0; S.res[j] = z; }
     }
     __syncwarp();
@@ -1945,7 +1945,7 @@ extern "C" int sse_prof_read(unsigned long long *out16) {
 }
 
 uint32_t sse_fused_max_line(void) { return TILE - 32u; }
-uint32_t sse_fused_tcache_words(void) { return 257u + TS_WORDS; }
+uint32_t sse_fused_tcache_words(void) { return 8192u; }   // (both engines' layouts fit)
 
 int sse_launch_fused(const KParams &p, void *stream, int sm_count, int device) {
     const uint32_t groups = (p.n_segs + PLAN_GROUP - 1) / PLAN_GROUP;

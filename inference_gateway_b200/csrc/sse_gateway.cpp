@@ -146,7 +146,8 @@ int ssegw_pump(ssegw *g) {
                 if (run->next == SSE_NONE) break;
                 run = &res.runs[run->next];
             }
-            if (s.mode & SSE_MODE_R) sse_agent_feed(s.agent, &res, k);
+            // a record the library could not decode (SSE_ERR_UNDECODED): the accumulators would be silently short, so the stream is failed
+            if ((s.mode & SSE_MODE_R) && sse_agent_feed(s.agent, &res, k) != SSE_OK) s.closed = true;
             if (res.segs[k].flags & SSE_SEG_TERMINATED) s.terminated = true;
             if (res.segs[k].flags & SSE_SEG_DEAD) s.closed = true;
         }
@@ -172,6 +173,17 @@ int ssegw_recv(ssegw *g, int id, uint8_t *buf, size_t cap, size_t *n) {
 }
 
 void ssegw_release_stream(ssegw *g, int id) { g->streams[(size_t)id].open = false; }
+
+// ---- handleStreamingRequest (api/routes.go:129-232): the raw proxy loop reads and writes in one goroutine
+int ssegw_proxy_stream(ssegw *g) { return ssegw_stream_chat_completions(g, SSE_MODE_P); }
+int ssegw_proxy_step(ssegw *g, int id, uint8_t *buf, size_t cap, size_t *n) {
+    for (;;) {
+        const int rc = ssegw_recv(g, id, buf, cap, n);
+        if (rc != 1) return rc;              // 0: nothing yet; -1: ReadBytes error / EOF, tail dropped (:187-195)
+        if (*n == 0) continue;               // :197-199
+        return 1;                            // :220-228 write + flush
+    }
+}
 
 // ---- mcp.Agent.RunWithStream view of a mode-R stream (one iteration)
 // Next element of the middleware channel: forwarded frames, then exactly one "data: [DONE]\n\n" once the iteration is

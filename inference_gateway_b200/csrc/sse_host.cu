@@ -99,7 +99,7 @@ KParams make_params(sse_ctx *c, Slot &s, uint32_t n_segs) {
     p.items = s.d_items; p.cap_items = c->cfg.max_recs; p.seg_term = s.d_segterm;
     p.items_sorted = s.d_items2; p.flags = c->cfg.flags;
     p.tiles = s.d_tiles; p.cap_tiles = c->cfg.max_segs + 64;
-    p.tcache = (c->cfg.flags & SSE_FLAG_NO_TEMPLATES) ? nullptr : c->d_tcache;
+    p.tcache = (c->cfg.flags & SSE_FLAG_TEMPLATES) ? c->d_tcache : nullptr;
     return p;
 }
 
@@ -125,13 +125,11 @@ int do_launch(sse_ctx *c, Slot &s, uint32_t n_segs, cudaStream_t st) {
     if (n_segs) {
         KParams p = make_params(c, s, n_segs);
         int e;
-        if (c->cfg.flags & SSE_FLAG_KERNEL_V1) { e = sse_launch_stream_kernel(p, (void *)st, c->sm_count); c->launches += 1; }
-        else if (c->cfg.flags & SSE_FLAG_KERNEL_V2) { e = sse_launch_stream_kernel_v2(p, (void *)st, c->sm_count, c->device); c->launches += 1; }
-        else if (!(c->cfg.flags & SSE_FLAG_KERNEL_SPLIT)) {   // default: plan + fused tile kernel
+        if (c->cfg.flags & SSE_FLAG_KERNEL_FUSED) {   // plan + single-pass tile kernel
             e = sse_launch_fused(p, (void *)st, c->sm_count, c->device);
             c->launches += 2;
         }
-        else {   // round-1 split pipeline produce -> decode -> finalize
+        else {   // default: produce -> sort -> decode (templates / automaton) -> finalize
             e = sse_launch_produce_kernel(p, (void *)st, c->sm_count);
             if (e == 0) e = sse_launch_decode_finalize(p, (void *)st, c->sm_count, c->device);
             c->launches += 6;   // produce, bucket hist/scan/scatter, decode, finalize
@@ -190,6 +188,7 @@ const char *sse_strerror(int status) {
     case SSE_ERR_BUSY: return "batch slot busy or in the wrong state";
     case SSE_ERR_OVERFLOW: return "result arena overflow: batch discarded (increase sse_config capacities)";
     case SSE_ERR_NOMEM: return "out of memory";
+    case SSE_ERR_UNDECODED: return "a line was not decoded (SSE_F_TOO_LONG / SSE_F_DEPTH_LIMIT): fold results are incomplete";
     default: return "unknown status";
     }
 }
@@ -217,7 +216,7 @@ void sse_worst_case_config(sse_config *cfg, uint32_t max_conns, uint32_t bytes_p
     sse_default_config(cfg, max_conns, bytes_per_batch);
     const uint64_t in = cfg->in_arena_bytes, cap = 0xF0000000ull;
     auto clamp = [&](uint64_t v) { return (uint32_t)(v > cap ? cap : v); };
-    cfg->carry_slot_bytes = sse_fused_max_line() & ~15u;             // longest line the fused kernel supports
+    cfg->carry_slot_bytes = 65536;                                   // longest supported line
     cfg->max_frames = clamp(in + 64);                                // a frame needs its own '\n' in this batch
     cfg->max_recs = clamp(in / 4 + 2ull * max_conns + 64);           // "data: x\n" is 8 bytes; one carried line per segment
     cfg->max_usages = cfg->max_recs;
@@ -232,6 +231,7 @@ int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
     if (cfg->n_slots < 1 || cfg->n_slots > 8 || cfg->max_conns == 0 || cfg->max_segs == 0 ||
         (cfg->in_arena_bytes & 15u) || cfg->carry_slot_bytes < 8192 + 16 || (cfg->carry_slot_bytes & 15u)) return SSE_ERR_ARG;
     if ((uint64_t)in_base_of(*cfg) + cfg->in_arena_bytes + 16 >= (1ull << 31)) return SSE_ERR_ARG;   // arena offsets are 31-bit
+    if (cfg->flags & ~(SSE_FLAG_KERNEL_FUSED | SSE_FLAG_COPY_OUT | SSE_FLAG_TEMPLATES)) return SSE_ERR_ARG;          // unknown engine flag
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) {
         cu_ok(cudaGetLastError(), "cudaGetDeviceCount");
@@ -244,13 +244,13 @@ int sse_init(int device, const sse_config *cfg, sse_ctx **out) {
     cudaDeviceProp prop;
     if (!cu_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete c; return SSE_ERR_CUDA; }
     c->sm_count = prop.multiProcessorCount;
-    if (cfg->flags & (SSE_FLAG_KERNEL_V2 | SSE_FLAG_KERNEL_SPLIT)) {
-        int e2 = sse_v2_prepare(device);
-        if (e2 != 0) { cu_ok((cudaError_t)e2, "sse_v2_prepare"); delete c; return SSE_ERR_CUDA; }
-    } else if (!(cfg->flags & SSE_FLAG_KERNEL_V1)) {
+    if (cfg->flags & SSE_FLAG_KERNEL_FUSED) {
         if (cfg->carry_slot_bytes > sse_fused_max_line()) { delete c; return SSE_ERR_ARG; }
         int e2 = sse_fused_prepare(device);
         if (e2 != 0) { cu_ok((cudaError_t)e2, "sse_fused_prepare"); delete c; return SSE_ERR_CUDA; }
+    } else {
+        int e2 = sse_v2_prepare(device);
+        if (e2 != 0) { cu_ok((cudaError_t)e2, "sse_v2_prepare"); delete c; return SSE_ERR_CUDA; }
     }
     bool ok = true;
     ok = ok && cu_ok(cudaStreamCreateWithFlags(&c->ctl_stream, cudaStreamNonBlocking), "cudaStreamCreate");

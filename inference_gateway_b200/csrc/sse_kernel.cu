@@ -127,7 +127,7 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                     if (consumed >= in_len) break;
                     continue;
                 }
-                if (!process_long_line(P, rc, slot, clen, mode)) { overflow = true; break; }
+                if (!process_long_line(P, rc, slot, clen, mode, SPLIT ? (int)s : -1)) { overflow = true; break; }
                 __syncwarp();
                 in_long = false; clen = 0; pos = q + 1;
             }
@@ -197,7 +197,7 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                             if (has_done) {
                                 // swallowed; still decoded for parseStreamingToolCalls (agent.go:182, :377-402)
                                 pay_s = pref ? a + 6 : a; pay_e = b;
-                                bool exact = (pay_e - pay_s) == 6 && is_done_at(buf + pay_s);
+                                bool exact = pref && (pay_e - pay_s) == 6 && is_done_at(buf + pay_s);   // only `data: [DONE]` ends A6's loop (agent.go:385-396)
                                 kind = exact ? K_DONE_EXACT : K_DONE; parse = 1;
                                 zc = (zero_copy && pay_s >= zc_lo) ? 1u : 0u;   // split: decoded in place by the decode kernel
                             } else if (pref && b - a > 6) {                  // agent.go:190-197
@@ -325,8 +325,7 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                         }
                         ParseOut po;
                         // (split pipeline: only exact "[DONE]" payloads get here, the sequential decoder is not part of that kernel)
-                        if (SPLIT || my_kind[h] == K_DONE_EXACT) { po.flags = 0; po.content_off = po.content_len = 0; po.tc_first = SSE_NONE; po.tc_count = po.n_choices = 0; po.usage = SSE_NONE; }
-                        else decode_chunk(cx, e.pay_s, e.pay_e, po);
+                        po.flags = 0; po.content_off = po.content_len = 0; po.tc_first = SSE_NONE; po.tc_count = po.n_choices = 0; po.usage = SSE_NONE;
                         sse_rec r;
                         r.frame = cx.emitted ? fb + pre_f[h] : SSE_NONE;
                         r.flags = po.flags;
@@ -441,5 +440,4 @@ static int launch_v1(const KParams &p, void *stream, int sm_count) {
     return (int)cudaGetLastError();
 }
 
-int sse_launch_stream_kernel(const KParams &p, void *stream, int sm_count) { return launch_v1<false>(p, stream, sm_count); }
 int sse_launch_produce_kernel(const KParams &p, void *stream, int sm_count) { return launch_v1<true>(p, stream, sm_count); }

@@ -20,10 +20,6 @@ namespace {
 
 using namespace ssetab;
 
-constexpr int V2_WARPS = 16;
-constexpr int V2_BUF = 6144;       // line window per warp
-constexpr int RING = 128;          // work items per warp
-constexpr int SEGSLOTS = 8;        // segments in flight per warp
 #ifndef SSE_ROUNDS
 #define SSE_ROUNDS 2
 #endif
@@ -37,37 +33,36 @@ constexpr int ROUNDS = SSE_ROUNDS;   // rounds between refills / busy checks
 constexpr int SKIPW = SSE_SKIPW;     // 16-byte windows a lane may cross per step while inside a long string value
 constexpr int KSTEPS = SSE_KSTEPS;   // plain automaton steps per round before the pending actions run
 
-struct SegSlot {
-    unsigned long long term;       // min over terminating lines of (rec << 32 | frame); ~0ull: none
-    uint32_t seg, conn;
-    int32_t pending;               // lines not yet decoded (+1 while the producer still owns the segment)
-    uint32_t used;
-    uint32_t rmode;
-    uint32_t pad;
+// ---- skeleton templates (see "templates" below): what the automaton records while it walks a line
+constexpr int TS_WORDS = 4096;             // template store (32-bit words)
+constexpr int NREC = 8, REC_MAX = 40;      // lanes recording at the same time; wildcards per template
+constexpr int T_BUCKETS = 64;              // buckets by the last two payload bytes (+ one for templates that end in a wildcard)
+enum : uint8_t { WK_END = 0, WK_STR = 1, WK_INT = 2 };
+enum : uint8_t { OP_NONE = 0, OP_CONTENT, OP_FINISH, OP_TC_ID, OP_TC_TYPE, OP_TC_NAME, OP_TC_ARGS, OP_TC_INDEX,
+                 OP_U_PROMPT, OP_U_COMPLETION, OP_U_TOTAL, OP_CHK_I64, OP_CHK_F32 };
+struct TRecEv { uint32_t start, len; uint8_t kind, op; uint16_t pad; };
+struct TRec { uint32_t n, nonsimple; TRecEv ev[REC_MAX]; };
+struct TCtx {                      // per CTA, shared memory
+    uint32_t store[TS_WORDS];
+    uint32_t head[T_BUCKETS + 1];
+    uint32_t used, rec_busy, build_lock, loaded;
+    TRec rec[NREC];
 };
+
 struct LaneScratch {               // cold per-lane state (usage ints, the tool-call element being assembled)
     int64_t u_prompt, u_completion, u_total, tc_index;
     uint32_t tc_flags, tc_dec;
     uint32_t id_off, id_len, type_off, type_len, name_off, name_len, args_off, args_len;
+    TRec *recp;                    // the automaton records this line's wildcards here (nullptr: not recording)
 };
-struct WarpSmem2 {
-    alignas(16) uint8_t buf[V2_BUF + 16];
-    LineEnt lt[LT_MAX];
-    uint16_t done_pos[DONE_MAX];
-    uint32_t done_cnt;
-    uint32_t ring_head, ring_tail;
-    uint32_t pad0;
-    uint4 ring[RING];              // src, len, rec, frame | slot << 29 (frame < 2^29)
-    SegSlot slots[SEGSLOTS];
-    LaneScratch ls[32];
-};
-struct CtaSmem2 {
-    DfaTables T;
-    WarpSmem2 w[V2_WARPS];
-};
-static_assert(sizeof(DfaTables) % 16 == 8 || sizeof(DfaTables) % 4 == 0, "tables are copied as 32-bit words");
-static_assert(sizeof(CtaSmem2) <= 227 * 1024, "shared memory budget");
-
+template <bool REC>
+__device__ __forceinline__ void rec_event(LaneScratch &S, uint32_t kind, uint32_t start, uint32_t len, uint32_t op) {
+    TRec *R = S.recp;
+    if (R->n < (uint32_t)REC_MAX) { TRecEv e; e.start = start; e.len = len; e.kind = (uint8_t)kind; e.op = (uint8_t)op; e.pad = 0; R->ev[R->n] = e; R->n++; }
+    else R->nonsimple = 1;
+}
+template <bool REC>
+__device__ __forceinline__ void rec_nonsimple(LaneScratch &S) { if (REC && S.recp) S.recp->nonsimple = 1; }
 // per-string flags (cleared outside strings) and per-line flags
 constexpr uint32_t SF_ESC = 1, SF_HI = 2, SF_UPPER = 4, SF_BAD = 8, SF_STRMASK = 15;
 constexpr uint32_t SF_SYN = 0x100, SF_TYPE = 0x200, SF_DEPTH = 0x400, SF_GBAD = 0x800, SF_USAGE = 0x1000,
@@ -152,9 +147,12 @@ __device__ void v2_elem_begin(const KParams &P, Lane &L, LaneScratch &S, LaneJob
     else L.cur = TY_INT;
 }
 
+template <bool REC>
 __device__ void v2_null(Lane &L, LaneScratch &S) {
     uint32_t ty = L.cur & 15u, tgt = (L.cur >> 9) & 15u;
     if (ty == TY_TS) { L.sf &= ~SF_GBAD; return; }
+    // a reset of captured state is not something a template replays
+    if (tgt == TG_CHOICES || (tgt == TG_USAGE && (L.sf & SF_USAGE)) || tgt == TG_TOOLCALLS || tgt == TG_TC_ID || tgt == TG_TC_TYPE || tgt == TG_TC_FUNCTION) rec_nonsimple<REC>(S);
     switch (tgt) {
     case TG_CHOICES:
         L.n_choices = 0; L.choices_count = 0; L.finish = SSE_FIN_NONE; L.content_off = L.content_len = 0;
@@ -174,10 +172,20 @@ __device__ void v2_null(Lane &L, LaneScratch &S) {
     }
 }
 
+template <bool REC>
 __device__ void v2_number_end(const KParams &P, Lane &L, LaneScratch &S, uint32_t end) {
     const uint32_t ty = L.cur & 15u, tgt = (L.cur >> 9) & 15u;
     const bool is_int = L.st == S_NZERO || L.st == S_NINT;
     const uint32_t start = end - L.slen - 1;
+    if (REC && S.recp && is_int) {
+        uint32_t op = OP_NONE;
+        if (ty == TY_INT) {
+            op = OP_CHK_I64;
+            if ((L.sf & SF_USAGE) && (tgt == TG_PROMPT || tgt == TG_COMPLETION || tgt == TG_TOTAL)) op = OP_U_PROMPT + (tgt - TG_PROMPT);
+            else if (tgt == TG_TC_INDEX && (L.sf & SF_TCOPEN) && lane_live(L) && L.tc_count <= 16u) op = OP_TC_INDEX | ((L.tc_count - 1u) << 4);
+        } else if (ty == TY_F32) op = OP_CHK_F32;
+        rec_event<REC>(S, WK_INT, start, end - start, op);
+    }
     if (ty == TY_INT) {
         if (!is_int) L.sf |= SF_TYPE;
         else if (end - start > 18 || tgt != TG_NONE) {
@@ -194,6 +202,7 @@ __device__ void v2_number_end(const KParams &P, Lane &L, LaneScratch &S, uint32_
 }
 
 // returns true when the current byte has to be looked up again in the new state
+template <bool REC>
 __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J, uint32_t t) {
     switch (t) {
     case A_OPEN_OBJ: case A_OPEN_ARR: {
@@ -216,8 +225,9 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
                 if (tgt != TG_NONE) {
                     if (tgt == TG_USAGE) L.sf |= SF_USAGE;
                     else if (tgt == TG_TC_FUNCTION) { if (live && (L.sf & SF_TCOPEN)) S.tc_flags |= SSE_TC_HAS_FUNC; }
-                    else if (tgt == TG_CHOICES) L.choices_count = 0;
+                    else if (tgt == TG_CHOICES) { if (L.n_choices || L.choices_count) rec_nonsimple<REC>(S); L.choices_count = 0; }
                     else if (tgt == TG_TOOLCALLS) {
+                        if (live && (L.sf & SF_TCNONNIL)) rec_nonsimple<REC>(S);
                         if (live) { L.sf = (L.sf | SF_TCNONNIL) & ~(SF_TCOPEN | SF_TCVALID); L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE; }
                     }
                 }
@@ -263,10 +273,16 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
     }
     case A_VSTR_END: {
         const uint32_t ty = L.cur & 15u, tgt = (L.cur >> 9) & 15u;
+        uint32_t op = OP_NONE;
         if (ty == TY_STR || ty == TY_PSTR) {
             if (tgt != TG_NONE && lane_live(L)) {
                 const uint32_t start = L.p - L.slen, len = L.slen;
                 const uint32_t d2 = ((L.sf & SF_ESC) ? 1u : 0u) | ((L.sf & SF_BAD) ? 2u : 0u);
+                if (tgt == TG_CONTENT) op = OP_CONTENT; else if (tgt == TG_FINISH) op = OP_FINISH;
+                else if ((L.sf & SF_TCOPEN) && (tgt == TG_TC_ID || tgt == TG_TC_TYPE || tgt == TG_NAME || tgt == TG_ARGS)) {
+                    if (L.tc_count <= 16u) op = (tgt == TG_TC_ID ? OP_TC_ID : tgt == TG_TC_TYPE ? OP_TC_TYPE : tgt == TG_NAME ? OP_TC_NAME : OP_TC_ARGS) | ((L.tc_count - 1u) << 4);
+                    else rec_nonsimple<REC>(S);
+                }
                 switch (tgt) {
                 case TG_CONTENT:
                     L.content_off = start; L.content_len = len;
@@ -290,19 +306,20 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
             }
         } else if (ty == TY_TS) L.sf &= ~SF_GBAD;
         else if (ty != TY_SKIP) L.sf |= SF_TYPE;
+        if (REC && S.recp) rec_event<REC>(S, WK_STR, L.p - L.slen, L.slen, op);
         value_done(L);
         return false;
     }
     case A_BAD_STAY: L.sf |= SF_BAD; L.st = S_VSTR; return false;
     case A_BAD_REDO: L.sf |= SF_BAD; L.st = S_VSTR; return true;
-    case A_NUM_END: v2_number_end(P, L, S, L.p); value_done(L); return true;
+    case A_NUM_END: v2_number_end<REC>(P, L, S, L.p); value_done(L); return true;
     case A_LIT_TRUE: case A_LIT_FALSE: {
         const uint32_t ty = L.cur & 15u;
         if (ty == TY_TS) L.sf |= SF_GBAD; else if (ty != TY_SKIP) L.sf |= SF_TYPE;
         value_done(L);
         return false;
     }
-    case A_LIT_NULL: v2_null(L, S); value_done(L); return false;
+    case A_LIT_NULL: v2_null<REC>(L, S); value_done(L); return false;
     case A_ELEM_REDO: v2_elem_begin(P, L, S, J); L.st = S_VAL; return true;
     case A_COMMA_ARR: v2_elem_begin(P, L, S, J); L.st = S_VAL; return false;
     default:   // A_ERR
@@ -312,11 +329,12 @@ __device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScr
 }
 
 // A line retires: final syntax check, record, termination bookkeeping (agent.go:205-242).
+template <bool REC>
 __device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
     bool terminates = false;
     if (!(L.sf & SF_SYN)) {
         if (L.depth == 0 && (L.st == S_NZERO || L.st == S_NINT || L.st == S_NFRAC || L.st == S_NEXP)) {
-            v2_number_end(P, L, S, L.pe);
+            v2_number_end<REC>(P, L, S, L.pe);
             L.st = S_END;
         }
         if (L.st != S_END) L.sf |= SF_SYN;
@@ -358,34 +376,8 @@ __device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJo
     return terminates;
 }
 
-// Called by whichever lane (or the producer) drops a segment's pending count to zero.
-__device__ void v2_finalize_segment(const KParams &P, SegSlot &sl) {
-    if (sl.term != ~0ull) {
-        const uint32_t trec = (uint32_t)(sl.term >> 32), tframe = (uint32_t)sl.term;
-        sse_seg_result r = P.seg_results[sl.seg];
-        sse_run *run = &r.run;
-        for (;;) {   // find the run that holds the terminating record; everything after it was never read by the reference
-            if (trec >= run->rec_first && trec < run->rec_first + run->rec_count) {
-                run->rec_count = trec - run->rec_first + 1;
-                run->frame_count = tframe - run->frame_first + 1;
-                run->next = SSE_NONE;
-                break;
-            }
-            if (run->next == SSE_NONE) break;
-            run = &P.runs[run->next];
-        }
-        r.flags |= SSE_SEG_TERMINATED;
-        r.carry_len = 0;
-        P.seg_results[sl.seg] = r;
-        ConnState ns; ns.carry_len = 0; ns.flags = CONN_FINISHED;
-        P.conns[sl.conn] = ns;
-    }
-    __threadfence_block();
-    sl.used = 0;
-}
-
 // One round of the per-lane automaton: KSTEPS plain steps, then the pending action (if any) of every lane.
-template <bool RO>
+template <bool RO, bool REC>
 __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J) {
     uint32_t pend = 0;                       // action | cls << 8 | in_str << 16 | in_tok << 17
     // phase A (once per round, only the lanes inside a long string value): jump to the next '"', '\\', control or non-ASCII
@@ -439,7 +431,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
         uint32_t t = pend & 0xFFu;
         const uint32_t cls = (pend >> 8) & 0xFFu;
         for (;;) {
-            if (!v2_action(P, T, L, S, J, t)) break;         // the action chose the next state
+            if (!v2_action<REC>(P, T, L, S, J, t)) break;         // the action chose the next state
             t = T.tr[L.st * NCLS + cls];                     // redo: same byte, new state
             if (t < A_FIRST) { L.st = t; break; }
         }
@@ -453,379 +445,6 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
     }
 }
 
-struct Producer {                  // warp-uniform coroutine state of the segment being produced
-    int phase;                     // 0 idle, 1 load window, 2 rounds, 3 done
-    uint32_t s, conn, mode, slot;
-    sse_seg seg;
-    int consumed, pend, base, fill, pos, clen;
-    bool in_long, dead, overflow, more;
-    RunChain rc;
-};
-
-__global__ void __launch_bounds__(V2_WARPS * 32, 1)
-sse_stream_kernel_v2(const __grid_constant__ KParams P, const DfaTables *__restrict__ gT) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    CtaSmem2 &cs = *reinterpret_cast<CtaSmem2 *>(smem_raw);
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(gT);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&cs.T);
-        for (int i = threadIdx.x; i < (int)(sizeof(DfaTables) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    WarpSmem2 &W = cs.w[threadIdx.x >> 5];
-    const uint32_t lane = lane_id();
-    if (lane == 0) { W.ring_head = W.ring_tail = 0; W.done_cnt = 0; }
-    if (lane < SEGSLOTS) { W.slots[lane].used = 0; W.slots[lane].pending = 0; W.slots[lane].term = ~0ull; }
-    __syncthreads();
-    const DfaTables &T = cs.T;
-    uint8_t *buf = W.buf;
-    LaneScratch &S = W.ls[lane];
-
-    Lane L; L.busy = false; L.p = L.pe = 0; L.win = make_uint4(0, 0, 0, 0);
-    L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.km = TRIE_ROOT; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
-    L.finish = 0; L.ct = L.ct1 = L.sstk = 0; L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
-    L.rec = L.frame = L.slot = L.plen = 0;
-
-    Producer pr; pr.phase = 0; pr.more = true;
-    uint32_t head = 0, tail = 0;     // ring indices (warp-uniform registers mirror of W.ring_*)
-
-    for (;;) {
-        __syncwarp();
-        // ------------------------------------------------------------------ produce when lanes would starve
-        const unsigned idle_mask = __ballot_sync(FULL, !L.busy);
-        const uint32_t n_idle = __popc(idle_mask), avail = tail - head;
-        // lanes start new lines together (batch-synchronous refill): lines of one stream share their structure, so lanes
-        // that start together stay in lockstep and share the divergent action code
-        const bool all_idle = n_idle == 32;
-        bool want = all_idle && (avail < 32u) && (pr.phase != 0 || pr.more) && (RING - avail >= (uint32_t)LT_MAX);
-        if (want && pr.phase == 0) {
-            // a free segment slot?
-            int fs = -1;
-            if (lane == 0) for (int k = 0; k < SEGSLOTS; k++) if (!W.slots[k].used) { fs = k; break; }
-            fs = __shfl_sync(FULL, fs, 0);
-            if (fs < 0) want = false;
-            else {
-                uint32_t s = 0;
-                if (lane == 0) s = atomicAdd(&P.ctr->ticket, 1u);
-                s = __shfl_sync(FULL, s, 0);
-                if (s >= P.n_segs) { pr.more = false; want = false; }
-                else {
-                    pr.s = s; pr.seg = P.segs[s]; pr.mode = pr.seg.mode; if (pr.mode & SSE_MODE_R) pr.mode |= SSE_MODE_PARSE;
-                    pr.conn = pr.seg.conn; pr.slot = (uint32_t)fs;
-                    pr.rc.have_first = false; pr.rc.last_idx = SSE_NONE;
-                    pr.rc.first.frame_first = pr.rc.first.frame_count = pr.rc.first.rec_first = pr.rc.first.rec_count = 0; pr.rc.first.next = SSE_NONE;
-                    const ConnState cst = P.conns[pr.conn];
-                    if (cst.flags & (CONN_FINISHED | CONN_DEAD)) {
-                        if (lane == 0) {
-                            sse_seg_result r; r.run = pr.rc.first; r.carry_len = cst.carry_len;
-                            r.flags = (cst.flags & CONN_DEAD) ? SSE_SEG_DEAD : SSE_SEG_FINISHED; r.reserved = 0;
-                            P.seg_results[s] = r;
-                        }
-                        continue;
-                    }
-                    if (lane == 0) {
-                        SegSlot &sl = W.slots[fs];
-                        sl.used = 1; sl.seg = s; sl.conn = pr.conn; sl.pending = 1; sl.term = ~0ull; sl.rmode = (pr.mode & SSE_MODE_R) ? 1u : 0u;
-                    }
-                    pr.in_long = (cst.flags & CONN_LONG) != 0;
-                    pr.clen = (int)cst.carry_len; pr.pend = 0; pr.consumed = 0; pr.dead = pr.overflow = false;
-                    if (!pr.in_long && pr.clen > 0) {
-                        const int A = (pr.clen + 15) & ~15;
-                        copy_g2s_bytes(buf + (A - pr.clen), P.carry + (size_t)pr.conn * P.carry_slot, pr.clen);
-                        pr.pend = pr.clen; pr.clen = 0;
-                    }
-                    pr.phase = 1;
-                    __syncwarp();
-                }
-            }
-        }
-        if (want && pr.phase != 0) {
-            uint8_t *slot_mem = P.carry + (size_t)pr.conn * P.carry_slot;
-            const int in_len = (int)pr.seg.in_len;
-            if (pr.phase == 1) {           // ---- load the next window
-                const int A = (pr.pend + 15) & ~15;
-                pr.base = A - pr.pend;
-                const int nload = min(in_len - pr.consumed, V2_BUF - A);
-                {
-                    const uint4 *g = reinterpret_cast<const uint4 *>(P.in + pr.seg.in_off + pr.consumed);
-                    uint4 *d = reinterpret_cast<uint4 *>(buf + A);
-                    const int nv = (nload + 15) >> 4;
-                    for (int i = lane; i < nv; i += 32) d[i] = __ldg(g + i);
-                }
-                pr.consumed += nload;
-                pr.fill = A + nload;
-                pr.pos = pr.base;
-                __syncwarp();
-                pr.phase = 2;
-                if (pr.in_long) {
-                    int q = -1;
-                    for (int i0 = pr.base; i0 < pr.fill && q < 0; i0 += 32) {
-                        int i = i0 + (int)lane;
-                        unsigned m = __ballot_sync(FULL, i < pr.fill && buf[i] == '\n');
-                        if (m) q = i0 + __ffs(m) - 1;
-                    }
-                    const int take = (q < 0) ? (pr.fill - pr.base) : (q - pr.base + 1);
-                    if (pr.clen + take > (int)P.carry_slot) { pr.dead = true; pr.phase = 3; }
-                    else {
-                        copy_s2g_bytes(slot_mem + pr.clen, buf + pr.base, take);
-                        pr.clen += take;
-                        __syncwarp();
-                        if (q < 0) { pr.pend = 0; pr.phase = (pr.consumed >= in_len) ? 3 : 1; }
-                        else {
-                            if (!process_long_line(P, pr.rc, slot_mem, pr.clen, pr.mode)) { pr.overflow = true; pr.phase = 3; }
-                            __syncwarp();
-                            pr.in_long = false; pr.clen = 0; pr.pos = q + 1;
-                        }
-                    }
-                }
-            } else if (pr.phase == 2) {    // ---- one round of up to LT_MAX lines
-                const uint32_t mode = pr.mode;
-                const int pos = pr.pos, fill = pr.fill;
-                if (lane == 0) W.done_cnt = 0;
-                __syncwarp();
-                int n_lines = 0;
-                for (int g0 = pos & ~15; g0 < fill && n_lines < LT_MAX; g0 += 512) {
-                    int off = g0 + (int)lane * 16;
-                    uint32_t nlm = 0, brm = 0;
-                    if (off < fill) {
-                        uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
-                        nlm = eqmask16(v, 0x0A0A0A0Au);
-                        if (mode & SSE_MODE_R) brm = eqmask16(v, 0x5B5B5B5Bu);
-                        uint32_t valid = 0xFFFFu;
-                        if (off < pos) valid &= 0xFFFFu << (pos - off);
-                        if (off + 16 > fill) valid &= 0xFFFFu >> (off + 16 - fill);
-                        nlm &= valid; brm &= valid;
-                    }
-                    while (brm) {
-                        int bpos = off + __ffs(brm) - 1;
-                        brm &= brm - 1;
-                        if (bpos + 6 <= fill && is_done_at(buf + bpos)) {
-                            uint32_t k = atomicAdd(&W.done_cnt, 1u);
-                            if (k < DONE_MAX) W.done_pos[k] = (uint16_t)bpos;
-                        }
-                    }
-                    uint32_t cnt = __popc(nlm), pre = cnt;
-                    #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(FULL, pre, d); if ((int)lane >= d) pre += t; }
-                    uint32_t total = __shfl_sync(FULL, pre, 31);
-                    uint32_t idx = (uint32_t)n_lines + pre - cnt;
-                    while (nlm) {
-                        int bpos = off + __ffs(nlm) - 1;
-                        nlm &= nlm - 1;
-                        if (idx < LT_MAX) W.lt[idx].nl = (uint16_t)bpos;
-                        idx++;
-                    }
-                    n_lines += (int)total;
-                }
-                __syncwarp();
-                if (n_lines == 0) {
-                    // ---- window exhausted: tail handling
-                    const int tail_len = fill - pos;
-                    if (pr.consumed >= in_len) {
-                        if (tail_len > (int)P.carry_slot) pr.dead = true;
-                        else { if (tail_len > 0) copy_s2g_bytes(slot_mem, buf + pos, tail_len); pr.clen = tail_len; }
-                        pr.phase = 3;
-                    } else if (tail_len >= V2_BUF - 32) {
-                        if (tail_len > (int)P.carry_slot) { pr.dead = true; pr.phase = 3; }
-                        else { copy_s2g_bytes(slot_mem, buf + pos, tail_len); pr.clen = tail_len; pr.in_long = true; pr.pend = 0; pr.phase = 1; }
-                    } else {
-                        // move the tail to the front so that it ends at a 16-byte aligned offset (pos > 32 > destination here)
-                        const int A2 = (tail_len + 15) & ~15;
-                        uint8_t *d = buf + (A2 - tail_len);
-                        const uint8_t *sp = buf + pos;
-                        if (d != sp) {
-                            for (int i0 = 0; i0 < tail_len; i0 += 32) {
-                                int i = i0 + (int)lane;
-                                uint8_t v = (i < tail_len) ? sp[i] : (uint8_t)0;
-                                __syncwarp();
-                                if (i < tail_len) d[i] = v;
-                                __syncwarp();
-                            }
-                        }
-                        pr.pend = tail_len; pr.phase = 1;
-                    }
-                    __syncwarp();
-                } else {
-                    if (n_lines > LT_MAX) n_lines = LT_MAX;
-                    const bool done_ovf = W.done_cnt > DONE_MAX;
-                    const int n_done = min((int)W.done_cnt, DONE_MAX);
-                    uint32_t my_flen[2] = { 0, 0 }, my_kind[2] = { 0, 0 }, my_parse[2] = { 0, 0 };
-                    #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        int i = (int)lane + 32 * h;
-                        if (i < n_lines) {
-                            int ls = (i == 0) ? pos : (int)W.lt[i - 1].nl + 1;
-                            int nl = W.lt[i].nl;
-                            int a = ls, b = nl + 1;
-                            uint32_t kind, parse = 0; int src_s = ls, pay_s = ls, pay_e = ls, flen = 0;
-                            if (mode & SSE_MODE_R) {
-                                trim_space(buf, a, b);
-                                bool has_done = false;
-                                for (int k = 0; k < n_done; k++) { int d = W.done_pos[k]; if (d >= a && d + 6 <= b) has_done = true; }
-                                if (done_ovf && !has_done) for (int k = a; k + 6 <= b; k++) if (is_done_at(buf + k)) { has_done = true; break; }
-                                bool pref = is_data_prefix(buf + a, b - a);
-                                if (has_done) {
-                                    pay_s = pref ? a + 6 : a; pay_e = b;
-                                    bool exact = (pay_e - pay_s) == 6 && is_done_at(buf + pay_s);
-                                    kind = exact ? K_DONE_EXACT : K_DONE; parse = 1;
-                                } else if (pref && b - a > 6) {
-                                    kind = K_EMIT; src_s = a; pay_s = a + 6; pay_e = b; flen = (b - a) + 2; parse = 1;
-                                } else kind = K_DROP;
-                            } else {
-                                kind = K_EMIT; src_s = ls; flen = nl + 1 - ls;
-                                if ((mode & SSE_MODE_PARSE) && is_data_prefix(buf + ls, nl + 1 - ls)) { parse = 1; pay_s = ls + 6; pay_e = nl; }
-                            }
-                            LineEnt &e = W.lt[i];
-                            e.src_s = (uint16_t)src_s; e.pay_s = (uint16_t)pay_s; e.pay_e = (uint16_t)pay_e;
-                            e.flen = (uint16_t)flen; e.kind = (uint8_t)kind; e.parse = (uint8_t)parse;
-                            my_flen[h] = (uint32_t)flen; my_kind[h] = kind; my_parse[h] = parse;
-                        }
-                    }
-                    uint32_t pre_b[2], pre_f[2], pre_r[2], pre_q[2], tot_b = 0, tot_f = 0, tot_r = 0, tot_q = 0;
-                    #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        uint32_t vb = my_flen[h], vf = my_flen[h] ? 1u : 0u, vr = my_parse[h];
-                        uint32_t vq = (my_parse[h] && my_kind[h] == K_EMIT) ? 1u : 0u;
-                        uint32_t sb = vb, sf = vf | (vr << 8) | (vq << 16);   // three small counters in one scan
-                        #pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            uint32_t tb = __shfl_up_sync(FULL, sb, d), tf = __shfl_up_sync(FULL, sf, d);
-                            if ((int)lane >= d) { sb += tb; sf += tf; }
-                        }
-                        pre_b[h] = tot_b + sb - vb;
-                        pre_f[h] = tot_f + (sf & 0xFF) - vf; pre_r[h] = tot_r + ((sf >> 8) & 0xFF) - vr; pre_q[h] = tot_q + ((sf >> 16) & 0xFF) - vq;
-                        const uint32_t lb = __shfl_sync(FULL, sb, 31), lf = __shfl_sync(FULL, sf, 31);
-                        tot_b += lb; tot_f += lf & 0xFF; tot_r += (lf >> 8) & 0xFF; tot_q += (lf >> 16) & 0xFF;
-                    }
-                    uint32_t ob = 0, fb = 0, rb = 0;
-                    if (lane == 0) {
-                        if (tot_b) ob = atomicAdd(&P.ctr->out_bytes, (tot_b + 15u) & ~15u);   // keep every round 16-byte aligned
-                        if (tot_f) fb = atomicAdd(&P.ctr->n_frames, tot_f);
-                        if (tot_r) rb = atomicAdd(&P.ctr->n_recs, tot_r);
-                        if (tot_q) atomicAdd(&W.slots[pr.slot].pending, (int)tot_q);
-                    }
-                    ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0);
-                    if (ob + tot_b + 16 > P.cap_out || fb + tot_f > P.cap_frames || rb + tot_r > P.cap_recs || fb + tot_f >= (1u << 29)) {
-                        if (lane == 0) { sse_overflow(P.ctr, SSE_OVF_OUT); if (tot_q) atomicSub(&W.slots[pr.slot].pending, (int)tot_q); }
-                        pr.overflow = true; pr.phase = 3;
-                    } else {
-                        #pragma unroll
-                        for (int h = 0; h < 2; h++)
-                            if (my_flen[h]) { sse_frame f; f.off = ob + pre_b[h]; f.len = my_flen[h]; P.frames[fb + pre_f[h]] = f; }
-                        __syncwarp();
-                        {   // warp-cooperative serializer
-                            uint32_t o = ob;
-                            for (int i = 0; i < n_lines; i++) {
-                                const LineEnt e = W.lt[i];
-                                if (!e.flen) continue;
-                                uint8_t *dst = P.out + o;
-                                const uint8_t *sp = buf + e.src_s;
-                                if (mode & SSE_MODE_R) {
-                                    const int body = (int)e.flen - 2;     // "data: " + payload, contiguous in the window
-                                    copy_s2g_vec(dst, sp, body);
-                                    if (lane < 2) dst[body + lane] = (uint8_t)'\n';
-                                } else copy_s2g_vec(dst, sp, (int)e.flen);
-                                o += e.flen;
-                            }
-                        }
-                        // work items for the consumer lanes; swallowed [DONE] lines are decoded here (rare)
-                        #pragma unroll 1
-                        for (int h = 0; h < 2; h++) {
-                            int i = (int)lane + 32 * h;
-                            if (i < n_lines && my_parse[h]) {
-                                const LineEnt e = W.lt[i];
-                                if (my_kind[h] == K_EMIT) {
-                                    const uint32_t plen = (uint32_t)(e.pay_e - e.pay_s);
-                                    uint4 it;
-                                    it.x = ob + pre_b[h] + (uint32_t)(e.pay_s - e.src_s);
-                                    it.y = plen;
-                                    it.z = rb + pre_r[h];
-                                    it.w = (fb + pre_f[h]) | (pr.slot << 29);
-                                    W.ring[(tail + pre_q[h]) & (RING - 1)] = it;
-                                } else {
-                                    sse_rec r;
-                                    r.frame = SSE_NONE; r.content_off = r.content_len = 0; r.tc_first = SSE_NONE; r.tc_count = 0; r.n_choices = 0;
-                                    r.usage = SSE_NONE; r.payload_len = (uint32_t)(e.pay_e - e.pay_s);
-                                    if (my_kind[h] == K_DONE_EXACT) r.flags = SSE_F_DONE_LINE | SSE_F_DONE_EXACT;
-                                    else {
-                                        ParseCtx cx; cx.sm = buf; cx.P = &P; cx.S = &c_schema; cx.emitted = false; cx.out_delta = 0;
-                                        ParseOut po;
-                                        decode_chunk(cx, e.pay_s, e.pay_e, po);
-                                        r.flags = po.flags | SSE_F_DONE_LINE;
-                                        r.content_off = po.content_off; r.content_len = po.content_len;
-                                        r.tc_first = po.tc_first; r.tc_count = (uint16_t)min(po.tc_count, 0xFFFFu);
-                                        r.n_choices = (uint16_t)min(po.n_choices, 0xFFFFu); r.usage = po.usage;
-                                    }
-                                    P.recs[rb + pre_r[h]] = r;
-                                }
-                            }
-                        }
-                        __threadfence_block();
-                        __syncwarp();
-                        tail += tot_q;
-                        append_run(P, pr.rc, fb, tot_f, rb, tot_r);
-                        pr.pos = (int)W.lt[n_lines - 1].nl + 1;
-                    }
-                }
-            }
-            if (pr.phase == 3) {           // ---- segment finished: connection state + draft result, release the slot's bias
-                if (lane == 0) {
-                    ConnState ns;
-                    ns.carry_len = pr.dead ? 0u : (uint32_t)pr.clen;
-                    ns.flags = (pr.dead ? CONN_DEAD : 0u) | ((pr.in_long && !pr.dead) ? CONN_LONG : 0u);
-                    P.conns[pr.conn] = ns;
-                    sse_seg_result r; r.run = pr.rc.first; r.carry_len = ns.carry_len;
-                    r.flags = pr.dead ? (SSE_SEG_LINE_TOO_LONG | SSE_SEG_DEAD) : 0u; r.reserved = 0;
-                    P.seg_results[pr.s] = r;
-                    __threadfence_block();
-                    SegSlot &sl = W.slots[pr.slot];
-                    if (atomicSub(&sl.pending, 1) == 1) v2_finalize_segment(P, sl);
-                }
-                __syncwarp();
-                pr.phase = 0;
-            }
-            continue;
-        }
-        // ------------------------------------------------------------------ nothing to produce: finished?
-        if (avail == 0 && n_idle == 32) {
-            if (pr.phase == 0 && !pr.more) break;
-            // all lanes idle, ring empty, but the producer could not run (ring space / slots): cannot happen with an
-            // empty ring, except when every segment slot is still marked used by a finalize in flight
-            continue;
-        }
-        // ------------------------------------------------------------------ idle lanes take work items
-        if (all_idle) {
-            const uint32_t rank = lane;
-            if (rank < avail) {
-                const uint4 it = W.ring[(head + rank) & (RING - 1)];
-                L.p = it.x; L.pe = it.x + it.y; L.rec = it.z; L.frame = it.w & 0x1FFFFFFFu;
-                L.slot = it.w >> 29; L.plen = it.y;
-                L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.km = TRIE_ROOT; L.slen = 0;
-                L.sf = W.slots[it.w >> 29].rmode ? SF_RMODE : 0u;
-                L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
-                L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
-                S.u_prompt = S.u_completion = S.u_total = 0;
-                L.busy = true;
-                if (L.p < L.pe) L.win = ldwin16<false>(P.out, L.p);
-            }
-        }
-        if (all_idle) head += min(avail, 32u);
-        // ------------------------------------------------------------------ automaton: rounds of K plain steps, then
-        // every lane that stopped at an action runs it (all lanes dispatch together: the divergent part is shared)
-        #pragma unroll 1
-        for (int round = 0; round < ROUNDS; round++) {
-            v2_round<false>(P, T, L, S, nullptr);
-            if (L.busy && L.p >= L.pe) {
-                SegSlot &sl = W.slots[L.slot];
-                if (v2_finish_line(P, L, S, nullptr)) atomicMin(&sl.term, ((unsigned long long)L.rec << 32) | L.frame);
-                __threadfence_block();
-                if (atomicSub(&sl.pending, 1) == 1) v2_finalize_segment(P, sl);
-                L.p = L.pe = 0;
-            }
-        }
-    }
-}
-
-
 // ---------------------------------------------------------------- split pipeline, stage 2: decode
 // Persistent warps pull 32 work items at a time (lines of the same stream are adjacent, so the lanes of a batch walk
 // near-identical structure in lockstep); no producer code and no line window in this kernel: small instruction
@@ -835,13 +454,286 @@ sse_stream_kernel_v2(const __grid_constant__ KParams P, const DfaTables *__restr
 #endif
 constexpr int V3_WARPS = SSE_V3_WARPS;
 
+// ---------------------------------------------------------------- skeleton templates
+// Consecutive chunks of a stream -- and the chunks of every other stream of the same provider -- differ only inside string
+// values and integers: keys, punctuation and literals are byte for byte the same. A line the automaton has walked leaves a
+// template in the CTA's cache (handed from launch to launch through KParams.tcache): its bytes outside those wildcards, in
+// runs, and per wildcard what the parse did with it. A later line whose runs compare equal, and whose wildcards are again a
+// well-formed string body / an integer, takes the automaton through exactly the same transitions: its record is the template's
+// with its own spans, and the automaton does not have to run. The work items are sorted by shape, so the 32 lanes of a warp
+// hold lines of the same template and walk it in step.
+//   [0] next | bucket << 16        [1] skeleton bytes | flags << 16 | tc_count << 24     [2] static record flags
+//   [3] n_choices | n_items << 16  [4] the last (up to 4) skeleton bytes  [5] their mask
+//   n_items items (run length | wildcard kind << 16 | op << 24), 4 words of per-element tool-call flags when tc_count > 0,
+//   then the runs (each starts on a word)
+constexpr uint32_t T_LIT_MAX = 1024, TF_HAS_USAGE = 1, TF_SIMPLE = 2, T_HDR = 6;
+
+__device__ __forceinline__ uint32_t gload4(const uint8_t *base, uint32_t off) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(base + (off & ~3u));
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), (off & 3u) * 8u);
+}
+__device__ __forceinline__ uint32_t nondigit4(uint32_t w4) {      // 0x80 in every byte that is not '0'..'9'
+    return (~((w4 | 0x80808080u) - 0x30303030u) | (w4 + 0x46464646u) | w4) & 0x80808080u;
+}
+// body of a string value from fp (just behind the opening quote): position of the closing quote, or SSE_NONE when the body
+// is not well formed (control byte, bad escape, no closing quote). d2: bit 0 escapes, bit 1 invalid UTF-8.
+// 0x80 in some byte of w iff w holds a '"', a '\\', a byte < 0x20 or a byte >= 0x80 (which byte: special_mask4)
+__device__ __forceinline__ uint32_t special_any4(uint32_t w) {
+    const uint32_t q = w ^ 0x22222222u, b = w ^ 0x5C5C5C5Cu;
+    return (((q - 0x01010101u) & ~q) | ((b - 0x01010101u) & ~b) | ((w - 0x20202020u) & ~w) | w) & 0x80808080u;
+}
+// position of the first special byte of the 16-byte window v at or after byte i (16: none)
+__device__ __forceinline__ uint32_t first_special16(const uint4 &v, uint32_t i) {
+    const uint32_t s0 = special_mask4(v.x), s1 = special_mask4(v.y), s2 = special_mask4(v.z), s3 = special_mask4(v.w);
+    unsigned long long lo = ((unsigned long long)s1 << 32) | s0, hi = ((unsigned long long)s3 << 32) | s2;
+    if (i < 8) lo &= ~0ull << (i * 8); else { lo = 0; hi &= ~0ull << ((i - 8) * 8); }
+    return lo ? (uint32_t)(__ffsll((long long)lo) - 1) >> 3 : (hi ? 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3) : 16u);
+}
+// body of a string value from fp (just behind the opening quote): position of the closing quote, or SSE_NONE when the body
+// is not well formed (control byte, bad escape, no closing quote). Returns d2 (bit 0 escapes, bit 1 invalid UTF-8) in the
+// two top bits of the result's companion word *d2p.
+__device__ __noinline__ uint32_t t_scan_string(const uint8_t *base, uint32_t fp, uint32_t pe, uint32_t *d2p) {
+    uint32_t p = fp, d2 = 0;
+    while (p < pe) {
+        uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + (p & ~15u)));
+        if ((p & 15u) == 0) {
+            // whole windows of plain bytes: two loads in flight, one test per window
+            uint4 v2 = __ldg(reinterpret_cast<const uint4 *>(base + p + 16u));
+            while (!(special_any4(v.x) | special_any4(v.y) | special_any4(v.z) | special_any4(v.w))) {
+                p += 16u;
+                if (p >= pe) { *d2p = d2; return SSE_NONE; }
+                v = v2;
+                v2 = __ldg(reinterpret_cast<const uint4 *>(base + p + 16u));
+            }
+        }
+        const uint32_t jb = first_special16(v, p & 15u);
+        const uint32_t q = (p & ~15u) + jb;
+        if (jb == 16u) { p = q; continue; }
+        if (q >= pe) break;
+        const uint32_t c = __ldg(base + q);
+        if (c == '"') { *d2p = d2; return q; }
+        if (c == '\\') {
+            const uint32_t c2 = __ldg(base + q + 1);
+            if (q + 2u <= pe && (c2 == '"' || c2 == '\\' || c2 == '/' || c2 == 'b' || c2 == 'f' || c2 == 'n' || c2 == 'r' || c2 == 't')) p = q + 2u;
+            else if (c2 == 'u' && q + 6u <= pe && hex4(base + q + 2u) >= 0) p = q + 6u;
+            else break;
+            d2 |= 1u;
+        } else if (c >= 0x80u) {
+            const int k = utf8_valid_len(base + q, (int)(pe - q));
+            if (k == 0) { d2 |= 2u; p = q + 1u; } else p = q + (uint32_t)k;      // invalid: the automaton flags it (A_BAD_*) and goes on byte by byte
+        } else break;                                // control byte
+    }
+    *d2p = d2;
+    return SSE_NONE;
+}
+// integer from fp: [-] 0 | [1-9][0-9]*; returns its end, or SSE_NONE
+__device__ __forceinline__ uint32_t t_scan_int(const uint8_t *base, uint32_t fp, uint32_t pe) {
+    uint32_t i = fp;
+    if (i < pe && __ldg(base + i) == '-') i++;
+    if (i >= pe) return SSE_NONE;
+    const uint32_t d0 = __ldg(base + i);
+    if (d0 == '0') return i + 1u;
+    if (d0 - '1' > 8u) return SSE_NONE;
+    i++;
+    while (i + 4u <= pe && nondigit4(gload4(base, i)) == 0) i += 4u;
+    while (i < pe && (uint32_t)__ldg(base + i) - '0' <= 9u) i++;
+    return i;
+}
+__device__ __noinline__ uint32_t t_finish_code(const uint8_t *base, uint32_t s, uint32_t len, uint32_t d2) {
+    if (len == 0) return SSE_FIN_NONE;
+    uint8_t tmp[40];
+    if (d2) { const uint32_t n = json_unquote(base, (int)s, (int)(s + len), tmp, 32); return (n <= 32) ? classify_finish(tmp, (int)n) : (uint32_t)SSE_FIN_OTHER; }
+    if (len > 32u) return SSE_FIN_OTHER;
+    for (uint32_t i = 0; i < len; i++) tmp[i] = __ldg(base + s + i);
+    return classify_finish(tmp, (int)len);
+}
+
+__device__ __forceinline__ void t_elem_begin(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J, uint32_t static_flags) {
+    if (L.sf & SF_TCOPEN) v2_flush_tc(P, L, S, J);
+    L.sf |= SF_TCOPEN; L.tc_count++;
+    S.tc_index = 0; S.tc_flags = static_flags; S.tc_dec = 0;
+    S.id_off = S.id_len = S.type_off = S.type_len = S.name_off = S.name_len = S.args_off = S.args_len = 0;
+}
+
+// Walk the line [ps, pe) along template T. APPLY = false: compare the runs, scan the wildcards, take content / finish_reason
+// (registers only); true: (after a successful compare) run every capture op into the lane state. SYNC: all lanes of the
+// warp are in the call (act: this lane has a line and a candidate) and meet after every item. Returns false when the line
+// does not fit. vflags: 0x80000000 an integer needs a range check (second walk).
+template <bool APPLY, bool SYNC>
+__device__ __forceinline__ bool t_walk(const KParams &P, const uint32_t *T, Lane &L, LaneScratch &S, LaneJobs *J, uint32_t ps, uint32_t pe,
+                                       uint32_t &vflags, bool act) {
+    const uint8_t *base = P.out;
+    const uint32_t n_items = act ? T[3] >> 16 : 0u, tc_count = act ? T[1] >> 24 : 0u;
+    const uint32_t *items = T + T_HDR;
+    const uint8_t *tc_static = reinterpret_cast<const uint8_t *>(items + n_items);
+    const uint32_t *lw = items + n_items + (tc_count ? 4u : 0u);
+    uint32_t fp = ps;
+    int cur_ord = -1;
+    bool ok = act;
+    if (!APPLY && act) { L.content_off = L.content_len = 0; L.finish = SSE_FIN_NONE; L.sf &= ~(SF_CDEC | SF_CBAD); }   // captures of an earlier candidate
+    #pragma unroll 1
+    for (uint32_t i = 0; ; i++) {
+        const bool go = ok && i < n_items;
+        if (SYNC) { if (!__any_sync(FULL, go)) break; } else if (!go) break;
+        if (go) {
+            const uint32_t it = items[i];
+            const uint32_t lit = it & 0xFFFFu, kind = (it >> 16) & 0xFFu, op = it >> 24;
+            if (!APPLY) {
+                uint32_t diff = fp + lit > pe ? 1u : 0u;
+                if (!diff) {
+                    uint32_t j = 0;
+                    #pragma unroll 4
+                    for (; j + 4u <= lit; j += 4u) diff |= gload4(base, fp + j) ^ lw[j >> 2];
+                    if (j < lit) diff |= (gload4(base, fp + j) ^ lw[j >> 2]) & ((1u << ((lit - j) * 8u)) - 1u);
+                }
+                if (diff) ok = false;
+            }
+            fp += lit; lw += (lit + 3u) >> 2;
+            if (kind == WK_END) { if (!APPLY && fp != pe) ok = false; }
+            else if (ok) {
+                uint32_t end, d2 = 0;
+                if (kind == WK_STR) end = t_scan_string(base, fp, pe, &d2); else end = t_scan_int(base, fp, pe);
+                if (end == SSE_NONE) ok = false;
+                else {
+                    const uint32_t code = op & 15u, ord = op >> 4, len = end - fp;
+                    if (!APPLY) {
+                        if (code == OP_CONTENT) {
+                            L.content_off = fp; L.content_len = len;
+                            L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
+                        } else if (code == OP_FINISH) L.finish = t_finish_code(base, fp, len, d2);
+                        else if ((code == OP_CHK_I64 || code == OP_CHK_F32) && len > 18u) vflags |= 0x80000000u;
+                    } else if (code != OP_NONE) {
+                        if (code >= OP_TC_ID && code <= OP_TC_INDEX)
+                            while (cur_ord < (int)ord) { cur_ord++; t_elem_begin(P, L, S, J, tc_static[cur_ord]); }
+                        int64_t v = 0;
+                        switch (code) {
+                        case OP_CONTENT:
+                            L.content_off = fp; L.content_len = len;
+                            L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
+                            break;
+                        case OP_FINISH: L.finish = t_finish_code(base, fp, len, d2); break;
+                        case OP_TC_ID: S.id_off = fp; S.id_len = len; S.tc_dec = (S.tc_dec & ~3u) | d2; break;
+                        case OP_TC_TYPE: S.type_off = fp; S.type_len = len; S.tc_dec = (S.tc_dec & ~12u) | (d2 << 2); break;
+                        case OP_TC_NAME: S.name_off = fp; S.name_len = len; S.tc_dec = (S.tc_dec & ~0x30u) | (d2 << 4); break;
+                        case OP_TC_ARGS: S.args_off = fp; S.args_len = len; S.tc_dec = (S.tc_dec & ~0xC0u) | (d2 << 6); break;
+                        case OP_TC_INDEX: if (parse_i64(base, (int)fp, (int)end, v)) S.tc_index = v; else L.sf |= SF_TYPE; break;
+                        case OP_U_PROMPT: if (parse_i64(base, (int)fp, (int)end, v)) S.u_prompt = v; else L.sf |= SF_TYPE; break;
+                        case OP_U_COMPLETION: if (parse_i64(base, (int)fp, (int)end, v)) S.u_completion = v; else L.sf |= SF_TYPE; break;
+                        case OP_U_TOTAL: if (parse_i64(base, (int)fp, (int)end, v)) S.u_total = v; else L.sf |= SF_TYPE; break;
+                        case OP_CHK_I64: if (len > 18u && !parse_i64(base, (int)fp, (int)end, v)) L.sf |= SF_TYPE; break;
+                        case OP_CHK_F32: if (len > 18u && f32_overflows(base, (int)fp, (int)end)) L.sf |= SF_TYPE; break;
+                        default: break;
+                        }
+                    }
+                    fp = end;
+                }
+            }
+        }
+        if (SYNC) __syncwarp();
+    }
+    if (APPLY && act) {                                // elements without captured fields, and the last element
+        while (cur_ord + 1 < (int)tc_count) { cur_ord++; t_elem_begin(P, L, S, J, tc_static[cur_ord]); }
+        if (L.sf & SF_TCOPEN) v2_flush_tc(P, L, S, J);
+    }
+    return ok;
+}
+
+__device__ __forceinline__ uint32_t t_bucket(const uint8_t *base, uint32_t ps, uint32_t pe) {
+    if (pe - ps < 2u) return 0u;
+    return ((uint32_t)__ldg(base + pe - 1u) * 31u + (uint32_t)__ldg(base + pe - 2u)) & (uint32_t)(T_BUCKETS - 1);
+}
+
+// Walk the chains: every lane of the warp tries its next candidate in the same iteration (warp-uniform loop), so lanes that
+// need more attempts do not fall out of step. off: first candidate per lane (0: none). Returns the template that fits.
+__device__ __forceinline__ uint32_t t_find(const KParams &P, TCtx &X, Lane &L, LaneScratch &S, uint32_t off, uint32_t &vflags) {
+    uint32_t found = 0;
+    const uint32_t plen = L.pe - L.p;
+    const uint32_t tail = plen >= 4u ? gload4(P.out, L.pe - 4u) : 0u;
+    #pragma unroll 1
+    while (__any_sync(FULL, off != 0u)) {
+        // candidates whose last skeleton bytes differ from the line's are passed over right here
+        while (off && (plen < 4u || ((tail ^ X.store[off + 4u]) & X.store[off + 5u]))) off = X.store[off] & 0xFFFFu;
+        uint32_t vf = 0;
+        const bool fit = t_walk<false, true>(P, X.store + off, L, S, nullptr, L.p, L.pe, vf, off != 0u);
+        if (off) {
+            if (fit) { found = off; off = 0; vflags = vf; }
+            else off = X.store[off] & 0xFFFFu;
+        }
+    }
+    return found;
+}
+
+// The automaton has just retired a line it recorded: turn the recording into a template (the caller holds the build lock).
+__device__ __noinline__ void t_build(const KParams &P, TCtx &X, const TRec &R, uint32_t ps, uint32_t pe, uint32_t rec_static, uint32_t tflags,
+                                     uint32_t n_choices, uint32_t tc_count, uint32_t tc_first) {
+    const uint8_t *base = P.out;
+    if (tc_count > 15u || pe - ps < 4u) return;
+    const uint32_t n_items = R.n + 1u;
+    uint32_t prev = ps, litw = 0, litb = 0;
+    for (uint32_t i = 0; i < R.n; i++) {
+        const uint32_t s = R.ev[i].start, e = s + R.ev[i].len;
+        if (s < prev || e > pe || s - prev > 0xFFFFu) return;
+        litw += (s - prev + 3u) >> 2; litb += s - prev; prev = e;
+    }
+    if (pe - prev > 0xFFFFu) return;
+    litw += (pe - prev + 3u) >> 2; litb += pe - prev;
+    if (litb > T_LIT_MAX) return;
+    const uint32_t words = T_HDR + n_items + (tc_count ? 4u : 0u) + litw;
+    const uint32_t off = X.used;
+    if (off + words > (uint32_t)TS_WORDS) return;
+    uint32_t *T = X.store + off;
+    {
+        const uint32_t endlit = pe - prev, tn = min(endlit, 4u);
+        const uint32_t tmask = tn == 4u ? 0xFFFFFFFFu : tn == 0u ? 0u : ~((1u << ((4u - tn) * 8u)) - 1u);     // the high tn bytes of the last word
+        T[4] = gload4(base, pe - 4u) & tmask; T[5] = tmask;
+        bool simple = !(tflags & TF_HAS_USAGE) && tc_count == 0;
+        for (uint32_t i = 0; i < R.n; i++) { const uint32_t c = R.ev[i].op & 15u; if (c != OP_NONE && c != OP_CONTENT && c != OP_FINISH && c != OP_CHK_I64 && c != OP_CHK_F32) simple = false; }
+        if (simple) tflags |= TF_SIMPLE;
+    }
+    const uint32_t endlit = pe - prev;
+    const uint32_t bucket = endlit >= 2u ? t_bucket(base, ps, pe) : (uint32_t)T_BUCKETS;      // ends in a wildcard: the catch-all chain
+    T[1] = litb | (tflags << 16) | (tc_count << 24); T[2] = rec_static; T[3] = n_choices | (n_items << 16);
+    uint32_t *items = T + T_HDR, *tcs = items + n_items, *lw = tcs + (tc_count ? 4u : 0u);
+    if (tc_count) {
+        uint32_t w4[4] = { 0, 0, 0, 0 }, t = tc_first;
+        for (uint32_t j = 0; j < tc_count && t != SSE_NONE; j++) { w4[j >> 2] |= (P.tcs[t].flags & 7u) << ((j & 3u) * 8u); t = P.tcs[t].next; }
+        tcs[0] = w4[0]; tcs[1] = w4[1]; tcs[2] = w4[2]; tcs[3] = w4[3];
+    }
+    prev = ps;
+    for (uint32_t i = 0; i < n_items; i++) {
+        const bool last = i + 1u == n_items;
+        const uint32_t s = last ? pe : R.ev[i].start;
+        const uint32_t lit = s - prev;
+        items[i] = lit | ((last ? (uint32_t)WK_END : (uint32_t)R.ev[i].kind) << 16) | ((last ? 0u : (uint32_t)R.ev[i].op) << 24);
+        for (uint32_t j = 0; j < lit; j += 4u) {
+            uint32_t v = gload4(base, prev + j);
+            if (lit - j < 4u) v &= (1u << ((lit - j) * 8u)) - 1u;
+            *lw++ = v;
+        }
+        prev = last ? pe : s + R.ev[i].len;
+    }
+    // the same skeleton may be there already (stored by another lane meanwhile): identical words
+    for (uint32_t o = X.head[bucket]; o; o = X.store[o] & 0xFFFFu) {
+        const uint32_t *U = X.store + o;
+        bool same = true;
+        for (uint32_t i = 1; i < words && same; i++) same = U[i] == T[i];
+        if (same) return;
+    }
+    T[0] = (bucket << 16) | (X.head[bucket] & 0xFFFFu);
+    __threadfence_block();
+    X.used = off + words;
+    X.head[bucket] = off;                                  // published: readers see a complete template
+}
+
 struct CtaSmem3 {
     DfaTables T;
+    TCtx X;
     LaneScratch ls[V3_WARPS * 32];
     LaneJobs jobs[V3_WARPS * 32];
 };
 static_assert(sizeof(CtaSmem3) <= 227 * 1024, "shared memory budget");
 
+template <bool TPL>
 __global__ void __launch_bounds__(V3_WARPS * 32, 1)
 sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict__ gT) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -851,12 +743,22 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
         uint32_t *dst = reinterpret_cast<uint32_t *>(&cs.T);
         for (int i = threadIdx.x; i < (int)(sizeof(DfaTables) / 4); i += blockDim.x) dst[i] = src[i];
     }
+    TCtx &X = cs.X;
+    const bool templates = TPL && P.tcache != nullptr;
+    {   // the templates learnt by earlier launches (a cache: results never depend on what it holds)
+        uint32_t loaded = 1;
+        if (templates) loaded = min(max(P.tcache[0], 1u), (uint32_t)TS_WORDS);
+        for (uint32_t i = threadIdx.x; i <= (uint32_t)T_BUCKETS; i += blockDim.x) X.head[i] = loaded > 1u ? P.tcache[1u + i] : 0u;
+        for (uint32_t i = threadIdx.x; i < loaded; i += blockDim.x) X.store[i] = loaded > 1u ? P.tcache[128u + i] : 0u;
+        if (threadIdx.x == 0) { X.used = loaded; X.loaded = loaded; X.rec_busy = 0; X.build_lock = 0; }
+    }
     __syncthreads();
     const DfaTables &T = cs.T;
     LaneScratch &S = cs.ls[threadIdx.x];
     LaneJobs *J = &cs.jobs[threadIdx.x];
     LaneJobs *Jw = &cs.jobs[threadIdx.x & ~31u];   // this warp's 32 queues
     J->n = 0;
+    S.recp = nullptr;
     const uint32_t lane = lane_id();
     const uint32_t n_items = min(P.ctr->n_items, P.cap_items);
 
@@ -871,26 +773,86 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
         base = __shfl_sync(FULL, base, 0);
         if (base >= n_items) break;
         const uint32_t idx = base + lane;
-        if (idx < n_items) {
+        const bool has = idx < n_items;
+        if (has) {
             const uint4 it = P.items_sorted[idx];
             L.p = it.x; L.plen = it.y & 0x00FFFFFFu; L.pe = it.x + L.plen; L.rec = it.z; L.slot = it.w;   // slot: segment index
             L.frame = P.recs[it.z].frame;
-           
             L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.km = TRIE_ROOT; L.slen = 0;
             L.sf = ((it.y & 0x80000000u) ? SF_RMODE : 0u) | ((it.y & 0x40000000u) ? SF_DONELINE : 0u);
             L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
             L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
             S.u_prompt = S.u_completion = S.u_total = 0;
+            S.recp = nullptr;
             L.busy = true;
-            if (L.p < L.pe) L.win = ldwin16<true>(P.out, L.p);
         }
-        while (__any_sync(FULL, L.busy)) {
+        // ---- a cached skeleton? the chain of the line's bucket first, then the catch-all chain
+        if (templates) {
+            const bool cand = has && L.plen >= 4u;
+            uint32_t vflags = 0, toff = 0;
+            uint32_t first = cand ? X.head[t_bucket(P.out, L.p, L.pe)] : 0u;
             #pragma unroll 1
-            for (int round = 0; round < ROUNDS; round++) {
-                v2_round<true>(P, T, L, S, J);
-                if (L.busy && L.p >= L.pe) {
-                    if (v2_finish_line(P, L, S, J)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
-                    L.p = L.pe = 0;
+            for (int pass = 0; pass < 2; pass++) {
+                const uint32_t f = t_find(P, X, L, S, first, vflags);
+                if (f) toff = f;
+                const bool miss = cand && !toff && pass == 0;
+                first = miss ? X.head[T_BUCKETS] : 0u;
+                if (!__any_sync(FULL, first != 0u)) break;
+            }
+            const uint32_t *Tm = X.store + toff;
+            const bool simple = toff && ((Tm[1] >> 16) & TF_SIMPLE) && !(vflags & 0x80000000u);
+            const bool full = toff && !simple;
+            if (__any_sync(FULL, full)) {              // usage / tool-call / range-check ops: a second walk runs them
+                if (full) {
+                    L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE; L.finish = SSE_FIN_NONE; L.content_off = L.content_len = 0;
+                    L.sf &= ~(SF_CDEC | SF_CBAD);
+                    if ((Tm[1] >> 16) & TF_HAS_USAGE) L.sf |= SF_USAGE;
+                }
+                uint32_t d = 0;
+                t_walk<true, true>(P, Tm, L, S, J, L.p, L.pe, d, full);
+            }
+            if (toff) {                                  // the record is written, the lane retires
+                L.n_choices = Tm[3] & 0xFFFFu;
+                if (Tm[2] & SSE_F_TC_NONNIL) L.sf |= SF_TCNONNIL;
+                L.st = S_END; L.depth = 0; L.p = L.pe;
+                if (v2_finish_line<false>(P, L, S, J)) atomicMin(&P.seg_term[L.slot], L.rec);
+                L.p = L.pe = 0;
+            } else if (cand) {
+                L.content_off = L.content_len = 0; L.finish = SSE_FIN_NONE; L.sf &= ~(SF_CDEC | SF_CBAD);      // (tried templates left captures behind)
+                if (!(L.sf & SF_DONELINE) && X.used + 360u <= (uint32_t)TS_WORDS) {     // the automaton takes the line: let it record a template
+                    uint32_t m = X.rec_busy;
+                    while ((~m) & ((1u << NREC) - 1u)) {
+                        const uint32_t b = (uint32_t)__ffs((~m) & ((1u << NREC) - 1u)) - 1u;
+                        const uint32_t old = atomicCAS(&X.rec_busy, m, m | (1u << b));
+                        if (old == m) { S.recp = &X.rec[b]; X.rec[b].n = 0; X.rec[b].nonsimple = 0; break; }
+                        m = old;
+                    }
+                }
+            }
+        }
+        if (L.busy && L.p < L.pe) L.win = ldwin16<true>(P.out, L.p);      // the automaton reads the payload through a 16-byte window
+        for (;;) {
+            const bool any_busy = __any_sync(FULL, L.busy);
+            if (any_busy) {
+                #pragma unroll 1
+                for (int round = 0; round < ROUNDS; round++) {
+                    v2_round<true, TPL>(P, T, L, S, J);
+                    if (L.busy && L.p >= L.pe) {
+                        const uint32_t ps = L.pe - L.plen, pe = L.pe;
+                        if (v2_finish_line<TPL>(P, L, S, J)) atomicMin(&P.seg_term[L.slot], L.rec);   // agent.go:235-242, resolved in stage 3
+                        if (TPL && S.recp) {            // keep the line's skeleton as a template (one lane builds at a time)
+                            TRec *R = S.recp;
+                            if (!R->nonsimple && !(L.sf & (SF_SYN | SF_TYPE | SF_DEPTH | SF_DONELINE)) && atomicCAS(&X.build_lock, 0u, 1u) == 0u) {
+                                t_build(P, X, *R, ps, pe, SSE_F_JSON_OK | ((L.sf & SF_TCNONNIL) ? SSE_F_TC_NONNIL : 0u), (L.sf & SF_USAGE) ? TF_HAS_USAGE : 0u,
+                                        L.n_choices, L.tc_count, L.tc_first);
+                                __threadfence_block();
+                                atomicExch(&X.build_lock, 0u);
+                            }
+                            atomicAnd(&X.rec_busy, ~(1u << (uint32_t)(R - X.rec)));
+                            S.recp = nullptr;
+                        }
+                        L.p = L.pe = 0;
+                    }
                 }
             }
             // strings that need unquoting were queued by the lanes: decode them with the whole warp
@@ -909,9 +871,23 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
                 if ((int)lane == leader) LJ.n = 0;
             }
             __syncwarp();
+            if (!any_busy) break;
+        }
+    }
+    // one CTA hands what it has learnt to the next launch (all CTAs see the same kinds of lines)
+    if (templates && blockIdx.x == 0) {
+        __syncthreads();
+        const uint32_t used = min(X.used, (uint32_t)TS_WORDS);
+        if (used > X.loaded) {
+            for (uint32_t i = threadIdx.x; i < used; i += blockDim.x) P.tcache[128u + i] = X.store[i];
+            for (uint32_t i = threadIdx.x; i <= (uint32_t)T_BUCKETS; i += blockDim.x) P.tcache[1u + i] = X.head[i];
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) P.tcache[0] = used;
         }
     }
 }
+
 
 
 // ---------------------------------------------------------------- split pipeline, stage 1b: order the work items
@@ -1040,27 +1016,20 @@ int sse_v2_prepare(int device) {
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(d, &T, sizeof T, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(sse_stream_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem2));
+    e = cudaFuncSetAttribute(sse_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(sse_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
+    e = cudaFuncSetAttribute(sse_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
     if (e != cudaSuccess) return (int)e;
     g_tables_dev[device] = d;
     return 0;
-}
-
-int sse_launch_stream_kernel_v2(const KParams &p, void *stream, int sm_count, int device) {
-    int grid = sm_count;   // persistent: one 16-warp CTA per SM
-    int need = (int)((p.n_segs + V2_WARPS - 1) / V2_WARPS);
-    if (need < grid) grid = need > 0 ? need : 1;
-    sse_stream_kernel_v2<<<grid, V2_WARPS * 32, sizeof(CtaSmem2), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
-    return (int)cudaGetLastError();
 }
 
 int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int device) {
     sse_bucket_hist_kernel<<<sm_count * 2, 512, 0, (cudaStream_t)stream>>>(p);
     sse_bucket_scan_kernel<<<1, SCAN_TPB, 0, (cudaStream_t)stream>>>(p);
     sse_bucket_scatter_kernel<<<sm_count * 2, SCATTER_TPB, 0, (cudaStream_t)stream>>>(p);
-    sse_decode_kernel<<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
+    if (p.tcache) sse_decode_kernel<true><<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
+    else sse_decode_kernel<false><<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const int tpb = 256;

@@ -23,6 +23,8 @@ class Gateway:
         L.ssegw_pump.argtypes = [vp]
         L.ssegw_recv.argtypes = [vp, i32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ssegw_agent_recv.argtypes = [vp, i32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.ssegw_proxy_stream.argtypes = [vp]
+        L.ssegw_proxy_step.argtypes = [vp, i32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.ssegw_release_stream.argtypes = [vp, i32]
         L.ssegw_release_stream.restype = None
         L.ssegw_agent_content.argtypes = [vp, i32]
@@ -74,6 +76,17 @@ class Gateway:
     def recv(self, sid: int):
         """One channel element, None if nothing is available yet; raises EOFError when the channel is closed."""
         return self._recv(self.L.ssegw_recv, sid)
+
+    def proxy_stream(self) -> int:
+        """handleStreamingRequest (api/routes.go:129-232): the raw /proxy stream."""
+        sid = self.L.ssegw_proxy_stream(self.g)
+        if sid < 0:
+            raise RuntimeError("no free connection slot")
+        return sid
+
+    def proxy_step(self, sid: int):
+        """One turn of the c.Stream callback: the line to write, None if none has arrived, EOFError when the loop ends."""
+        return self._recv(self.L.ssegw_proxy_step, sid)
 
     def agent_recv(self, sid: int):
         return self._recv(self.L.ssegw_agent_recv, sid)

@@ -15,7 +15,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "liborc.so")
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("sse_oracle.c", "sse_oracle.h", "orc_bench.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("sse_oracle.c", "sse_oracle.h", "orc_bench.c", "orc_check.c", "Makefile")]
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"], stdout=subprocess.DEVNULL)
@@ -92,6 +92,13 @@ def lib():
         _lib.orc_bench_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _lib.orc_bench_run.restype = C.c_double
+        _lib.orc_digest_init.argtypes = [C.c_void_p, C.c_size_t]
+        _lib.orc_digest_init.restype = None
+        _lib.orc_digest_streams.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_digest_streams.restype = None
+        _lib.orc_digest_result.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_digest_result.restype = C.c_uint32
     return _lib
 
 
@@ -254,3 +261,36 @@ def bench_run(arena, off, length, mode, n_threads: int, passes: int = 1):
     secs = L.orc_bench_run(arena.ctypes.data, off.ctypes.data, length.ctypes.data, mode.ctypes.data,
                            len(off), n_threads, passes, C.byref(ob), C.byref(fr), C.byref(ok))
     return secs, ob.value, fr.value, ok.value
+
+
+# ---------------------------------------------------------------- full-size parity digests (orc_check.c)
+def _digest_dtype():
+    import numpy as np
+    return np.dtype([("frames_h", "<u8"), ("recs_h", "<u8"), ("n_frames", "<u8"), ("n_recs", "<u8"), ("frame_bytes", "<u8"),
+                     ("inexact", "<u4"), ("pad", "<u4")])
+
+
+def new_digests(n: int):
+    import numpy as np
+    d = np.zeros(n, dtype=_digest_dtype())
+    lib().orc_digest_init(d.ctypes.data, n)
+    return d
+
+
+def digest_streams(arena, off, length, mode, n_threads: int):
+    """Oracle digests of whole bodies: arena uint8[], off uint64[], length uint32[], mode uint8[] (bit0 R, bit1 parse).
+    Returns (digests, terminated uint8[], tail_len uint32[])."""
+    import numpy as np
+    n = len(off)
+    d = new_digests(n)
+    term = np.zeros(n, dtype=np.uint8)
+    tail = np.zeros(n, dtype=np.uint32)
+    lib().orc_digest_streams(arena.ctypes.data, off.ctypes.data, length.ctypes.data, mode.ctypes.data, n, n_threads,
+                             d.ctypes.data, term.ctypes.data, tail.ctypes.data)
+    return d, term, tail
+
+
+def digest_result(raw_result, conn, digests, carry_len, seg_flags) -> int:
+    """Folds one sse_result (ctypes struct of the product's C ABI, passed by reference) into per-connection digests."""
+    return lib().orc_digest_result(C.addressof(raw_result), conn.ctypes.data, digests.ctypes.data, carry_len.ctypes.data,
+                                   seg_flags.ctypes.data)

@@ -694,7 +694,7 @@ static void r_line(void *u, const uint8_t *line, size_t n, size_t off) {
         if (has_prefix(t, tn, "data: ")) { dd = t + 6; dn = tn - 6; pref = 1; }
         /* A6 breaks only on `data: [DONE]` (:385-396: data == "[DONE]" after the "data: " case); a bare `[DONE]` line
          * takes the switch's default branch (line == "[DONE]" fails case 2) and is skipped, like any unparsable line */
-        if (pref && dn == 6 && !memcmp(dd, "[DONE]", 6)) l->kind = 4; /* exact: A6 breaks here */
+        if (pref && dn == 6 && !memcmp(dd, "[DONE]", 6)) l->kind = ORC_L_DONE_EXACT; /* exact: A6 breaks here */
         else { uint32_t ci = orc_unmarshal_chunk(r, dd, dn); r->lines[r->n_lines - 1].chunk = ci; }
         return;
     }

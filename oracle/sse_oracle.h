@@ -79,7 +79,8 @@ typedef struct {
 enum { ORC_L_DROPPED = 0,     /* R: not "data: "-prefixed / empty payload */
        ORC_L_EMITTED = 1,     /* P: every line; R: frame emitted */
        ORC_L_DONE = 2,        /* R: swallowed, Contains "[DONE]" (agent.go:181-184) */
-       ORC_L_UNREAD = 3 };    /* R: after the terminating chunk (agent.go:235-242) */
+       ORC_L_UNREAD = 3,      /* R: after the terminating chunk (agent.go:235-242) */
+       ORC_L_DONE_EXACT = 4 };/* R: swallowed, and the payload is exactly "[DONE]" (agent.go:394-396 breaks on it) */
 
 typedef struct {
     uint8_t  *out;     size_t out_len,  out_cap;

@@ -12,12 +12,12 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-@pytest.fixture(scope="session", params=["fused", "automaton", "copy", "split", "v1"])
+@pytest.fixture(scope="session", params=["split", "templates", "copy", "fused", "fused_templates"])
 def engine(request):
     """One GPU context per kernel generation (the product path: libssegpu.so through its C ABI).
-    split = produce / decode / finalize pipeline (default, zero-copy frames); copy = the same with SSE_FLAG_COPY_OUT; v2 = fused producer-consumer kernel; v1 = first generation."""
+    split = produce / sort / decode / finalize pipeline (default, zero-copy frames); templates = the same with skeleton-template replay; copy = default with SSE_FLAG_COPY_OUT; fused / fused_templates = the single-pass tile kernel."""
     from inference_gateway_b200 import SseEngine
     eng = SseEngine(device=0, max_conns=4096, bytes_per_batch=8 << 20, carry_slot_bytes=32768, n_slots=2,
-                    flags={"v1": 1, "split": 4, "fused": 0, "automaton": 16, "copy": 8}[request.param])
+                    flags={"split": 0, "fused": 4, "fused_templates": 4 | 16, "templates": 16, "copy": 8}[request.param])
     yield eng
     eng.close()

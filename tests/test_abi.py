@@ -57,6 +57,17 @@ def test_strerror_and_argument_checks():
     big.in_arena_bytes = 1 << 30
     big.out_arena_bytes = (1 << 30) + (1 << 29)
     assert L.sse_init(0, C.byref(big), C.byref(ctx)) == A.SSE_ERR_ARG
+    # unknown engine flags are refused (bit 0 was the first-generation kernel, bit 1 an earlier fused design: both removed)
+    for fl in (1, 2, 32, 1 << 31):
+        odd = A.Config()
+        L.sse_default_config(C.byref(odd), 1024, 1 << 20)
+        odd.flags = fl
+        assert L.sse_init(0, C.byref(odd), C.byref(ctx)) == A.SSE_ERR_ARG
+    # sse_worst_case_config: capacities that no batch of that many input bytes can overflow (one record per 4 bytes at most:
+    # "data: x\n" is 8 bytes, "\n" alone yields a frame but no record)
+    wc = A.Config()
+    L.sse_worst_case_config(C.byref(wc), 64, 1 << 20)
+    assert wc.struct_size == C.sizeof(A.Config) and wc.max_frames >= (1 << 20) and wc.max_recs >= (1 << 20) // 8
     # sse_at resolves both halves of the offset space
     res = A.Result()
     ob = (C.c_uint8 * 8)(*b"OUTARENA"); ib = (C.c_uint8 * 8)(*b"INPUTBUF")

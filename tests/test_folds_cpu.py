@@ -109,6 +109,12 @@ def _streams():
         b'data: {"choices":[{"delta":{},"finish_reason":"tool_calls"}]}\n\ndata: [DONE]\n\n',
         b'data: {"choices":[{"delta":{"tool_calls":[{"index":0,"id":"c","function":{"name":"n","arguments":"{}"}}]}}]}\n\ndata: [DONE]\n\n'
         b'data: {"choices":[{"delta":{"tool_calls":[{"index":1,"id":"after done","function":{"name":"ignored"}}]}}]}\n\n',
+        # a bare "[DONE]" line (no "data: " prefix) is swallowed (agent.go:181-184) but parseStreamingToolCalls only breaks on
+        # the exact line "data: [DONE]" (agent.go:394-396): the tool call that follows still counts
+        b'data: {"choices":[{"delta":{"tool_calls":[{"index":0,"id":"a","function":{"name":"first","arguments":"{"}}]}}]}\n\n[DONE]\n\n'
+        b'data: {"choices":[{"delta":{"tool_calls":[{"index":0,"function":{"arguments":"}"}},{"index":1,"id":"b","function":{"name":"second"}}]}}]}\n\n'
+        b'data: {"choices":[{"delta":{},"finish_reason":"tool_calls"}]}\n\n',
+        b'  [DONE]  \n\ndata: {"choices":[{"delta":{"tool_calls":[{"index":0,"id":"x","function":{"name":"n"}}]}}]}\n\n',
     ]
     return [b for b, _, _ in streams] + extra
 
@@ -143,3 +149,47 @@ def test_telemetry_fold_matches_oracle(in_arena):
         L.sse_telemetry_free(f)
         eusage, ecalls = orc.telemetry(v.out)
         assert (usage, calls) == (eusage, ecalls), body[:100]
+
+
+def test_mcp_path_telemetry_counts_the_final_done_frame():
+    """On the MCP path the client body is the forwarded frames plus the agent's own "data: [DONE]\\n\\n" (agent.go:140-143);
+    telemetry.go:195-198 looks at the last 4 pieces of THAT body, so the host feeds the synthetic frame too."""
+    L = A.load()
+    done = b"data: [DONE]\n\n"
+    usage_ev = b'data: {"choices":[],"usage":{"prompt_tokens":7,"completion_tokens":8,"total_tokens":15}}\n\n'
+    filler = b'data: {"choices":[{"delta":{"content":"x"}}]}\n\n'
+    stop = b'data: {"choices":[{"delta":{},"finish_reason":"stop"}]}\n\n'
+    seen = set()
+    for k in range(4):          # usage event followed by k more events and the terminating one
+        body = usage_ev + filler * k + stop
+        v = orc.reframe(body)
+        fr = FakeResult(v, True)
+        f = L.sse_telemetry_new()
+        A.check(L.sse_telemetry_feed(f, C.byref(fr.res), 0), "feed")
+        A.check(L.sse_telemetry_feed_bytes(f, done, len(done)), "feed_bytes")
+        rc, usage, calls = telemetry_results(L, f)
+        L.sse_telemetry_free(f)
+        eusage, ecalls = orc.telemetry(v.out + done)
+        assert rc == 0 and (usage, calls) == (eusage, ecalls), k
+        seen.add(usage)
+    assert seen == {(7, 8, 15), (0, 0, 0)}         # the window really moves: with enough later pieces the usage falls out
+    f = L.sse_telemetry_new()
+    assert L.sse_telemetry_feed_bytes(f, b"no newline", 10) == A.SSE_ERR_ARG
+    L.sse_telemetry_free(f)
+
+
+def test_folds_report_undecoded_records():
+    """A record flagged TOO_LONG / DEPTH_LIMIT is a line the reference would have decoded: the folds say so instead of
+    skipping it silently."""
+    L = A.load()
+    v = orc.reframe(b'data: {"choices":[{"delta":{"content":"a"}}]}\n\n')
+    for flag in (A.F_TOO_LONG, A.F_DEPTH_LIMIT):
+        fr = FakeResult(v, True)
+        fr.res.recs[0].flags = flag
+        f = L.sse_agent_new()
+        assert L.sse_agent_feed(f, C.byref(fr.res), 0) == A.SSE_ERR_UNDECODED
+        L.sse_agent_free(f)
+        t = L.sse_telemetry_new()
+        assert L.sse_telemetry_feed(t, C.byref(fr.res), 0) == A.SSE_ERR_UNDECODED
+        L.sse_telemetry_free(t)
+    assert b"not decoded" in L.sse_strerror(A.SSE_ERR_UNDECODED)

@@ -122,3 +122,65 @@ def test_mcp_writer_loop_terminal_frame_and_error_status(gw):
                        b'data: {"error": "upstream exploded"}\n\n'
                        b'data: {"choices":[{"index":0,"delta":{},"finish_reason":"stop"}]}\n\n'
                        b'data: [DONE]\n\n')       # the usage-only chunk after the terminating one is never read (agent.go:235-242)
+
+
+def test_raw_proxy_stream_loop(gw):
+    """api/routes.go:129-232 handleStreamingRequest: every '\\n'-terminated line of the upstream body is written as is (SSE
+    comments, event: lines, CRLF, blank separators, non-SSE bytes), in order; at EOF the unterminated tail is dropped
+    (:187-195) and the loop ends."""
+    sid = gw.proxy_stream()
+    body = (b": keep-alive\n\nevent: message\r\ndata: {\"x\":1}\r\n\r\n" + b"data: " + b"z" * 5000 + b"\n\n"
+            b"not sse at all\n\n\n" + b"data: [DONE]\n\nunterminated tail")
+    written = bytearray()
+    lines = []
+    for i in range(0, len(body), 997):                    # upstream TCP segments
+        piece = body[i:i + 997]
+        assert gw.upstream_write(sid, piece) == len(piece)
+        gw.pump()
+        while (e := gw.proxy_step(sid)) is not None:
+            lines.append(e); written += e
+    gw.upstream_close(sid)
+    gw.pump()
+    with pytest.raises(EOFError):
+        gw.proxy_step(sid)
+    gw.release(sid)
+    assert bytes(written) == body[:body.rfind(b"\n") + 1]
+    assert lines == [l + b"\n" for l in body.split(b"\n")[:-1]]      # one write (+ flush) per ReadBytes line
+
+
+def test_one_stream_of_blank_lines_cannot_starve_or_overflow_the_batch():
+    """Result capacities are sized for the worst case of the bytes a batch can hold (sse_worst_case_config): a connection that
+    sends nothing but '\\n' (one frame per byte) next to ordinary streams neither overflows the batch (which would fail every
+    stream in it) nor keeps the others from making progress; a stream with more pending bytes than a batch holds is taken
+    piecewise."""
+    g = Gateway(device=0, max_conns=8, bytes_per_batch=1 << 16)
+    try:
+        evil = g.proxy_stream()
+        good = [g.stream_chat_completions(R) for _ in range(3)]
+        ok_body = (b'data: {"choices":[{"index":0,"delta":{"content":"hi"},"finish_reason":null}]}\n\n'
+                   b'data: {"choices":[{"index":0,"delta":{},"finish_reason":"stop"}]}\n\n')
+        flood = b"\n" * 100000                              # > bytes_per_batch: the pump takes what fits, round after round
+        sent = 0
+        got_evil = 0
+        good_out = {s: [] for s in good}
+        for s in good:
+            assert g.upstream_write(s, ok_body) == len(ok_body)
+        for _ in range(400):
+            if sent < len(flood):
+                sent += g.upstream_write(evil, flood[sent:sent + 30000])
+            g.pump()
+            while (e := g.proxy_step(evil)) is not None:
+                assert e == b"\n"; got_evil += 1
+            for s in good:
+                try:
+                    while (e := g.agent_recv(s)) is not None:
+                        good_out[s].append(e)
+                except EOFError:
+                    pass
+            if got_evil == len(flood):
+                break
+        assert got_evil == len(flood)
+        for s in good:
+            assert len(good_out[s]) == 3 and good_out[s][-1] == b"data: [DONE]\n\n"
+    finally:
+        g.close()

@@ -115,6 +115,17 @@ def test_reference_fixtures_builder(engine, fx):
     assert got == fx["expect"]["parsed"]
 
 
+@pytest.mark.parametrize("fx", [f for f in GOLD if "frames" in f["expect"]], ids=lambda f: f["name"])
+def test_reference_fixtures_dropped_elements(engine, fx):
+    """tests/middlewares/mcp_test.go:537: an element without the "data: " prefix is dropped by the agent (agent.go:186-188)."""
+    bodies = list(_fixture_bodies(fx))
+    outs, views = _run_and_check(engine, bodies, [R] * len(bodies), n_batches=2, seed=3, folds=True)
+    for o in outs:
+        assert o.frames == [] and o.recs == [] and not o.terminated
+        content, has, term, fin, calls = agent_results(engine.L, o.agent)
+        assert content == b"" and not has and not term and calls == []
+
+
 # ------------------------------------------------------------------ BASELINE.json configs (reduced stream counts)
 @pytest.mark.parametrize("name,n_streams,n_batches", [
     ("C1", 1, 1), ("C1", 1, 9), ("C2", 256, 1), ("C2", 256, 4), ("C3", 256, 1), ("C3", 256, 5),
@@ -141,8 +152,13 @@ def test_mixed_modes_and_folds(engine):
             assert content == v.acc_content and has == v.has_tool_calls and term == v.terminated
             assert calls == orc.parse_tool_calls(v.builder)
             # telemetry over what the MCP path would have written (frames + final [DONE], mcp.go:253-299)
+            done = b"data: [DONE]\n\n"                                      # agent.go:140-143, written by the host
+            A.check(L.sse_telemetry_feed_bytes(o.tele, done, len(done)), "sse_telemetry_feed_bytes")
             rc, usage, tcalls = telemetry_results(L, o.tele)
-            # the fold saw only the frames; the reference body also carries "data: [DONE]\n\n" (2 more pieces)
+            eusage, ecalls = orc.telemetry(b"".join(o.frames) + done)       # telemetry.go:190-277 over the body the client got
+            assert rc == 0
+            assert usage == eusage, i
+            assert tcalls == ecalls, i
         elif m == PP:
             rc, usage, tcalls = telemetry_results(L, o.tele)
             eusage, ecalls = orc.telemetry(b"".join(o.frames))

@@ -72,6 +72,24 @@ def test_reference_fixture_builder(fx):
     assert got == fx["expect"]["parsed"]
 
 
+@pytest.mark.parametrize("fx", [f for f in GOLD if "frames" in f["expect"]], ids=lambda f: f["name"])
+def test_reference_fixture_dropped_elements(fx):
+    """Channel elements that are not "data: "-prefixed never reach the client (agent.go:186-188)."""
+    for body in _bodies(fx):
+        v = orc.reframe(body, append_done=True)
+        assert [l.kind for l in v.lines] == [orc.L_DROPPED] * len(v.lines)
+        assert v.out == b"data: [DONE]\n\n" * fx["expect"]["done_frames"]
+        assert v.terminated == fx["expect"]["terminated"] and v.acc_content.decode() == fx["expect"]["acc_content"]
+
+
+def test_every_sse_literal_of_the_reference_tests_is_a_fixture():
+    """tools/make_golden.py walks every *_test.go of the reference for string literals that hold SSE bytes and records the ones
+    no fixture contains: none."""
+    audit = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_fixtures.json")))["audit"]
+    assert audit["n_literals"] >= 70 and audit["uncovered"] == []
+    assert audit["files"] == ["tests/mcp_agent_test.go", "tests/middlewares/mcp_test.go"]
+
+
 def test_telemetry_quirks():
     # only the last 4 "\n\n" pieces are searched for usage (telemetry.go:195-198)
     u = b'data: {"usage":{"prompt_tokens":1,"completion_tokens":2,"total_tokens":3}}\n\n'

@@ -26,7 +26,7 @@ def rec_to_dict(res, ri: int) -> dict:
     fl = int(r["flags"])
     d = dict(flags=fl, json_ok=bool(fl & A.F_JSON_OK), done=bool(fl & A.F_DONE_LINE),
              done_exact=bool(fl & A.F_DONE_EXACT), terminates=bool(fl & A.F_TERMINATES),
-             too_long=bool(fl & (A.F_TOO_LONG | A.F_DEPTH_LIMIT)), frame=int(r["frame"]), payload_len=int(r["payload_len"]))
+             depth_limit=bool(fl & A.F_DEPTH_LIMIT), too_long=bool(fl & A.F_TOO_LONG), frame=int(r["frame"]), payload_len=int(r["payload_len"]))
     if d["json_ok"]:
         d["n_choices"] = int(r["n_choices"])
         d["finish"] = (fl & A.F_FINISH_MASK) >> A.F_FINISH_SHIFT
@@ -165,7 +165,9 @@ def check_stream(body: bytes, mode: int, o: ConnOut, label=""):
         assert g == e, f"{label}: frame {i} differs:\n gpu={g[:120]!r}\n ref={e[:120]!r}"
     assert len(o.recs) == len(exp_recs), f"{label}: {len(o.recs)} recs, oracle {len(exp_recs)}"
     for i, (g, e) in enumerate(zip(o.recs, exp_recs)):
-        if g.get("too_long"):
+        assert not g["too_long"], f"{label}: rec {i} was not decoded (SSE_F_TOO_LONG)"
+        if g["depth_limit"]:      # nesting deeper than 128 levels: the documented limit, reported as not JSON_OK
+            assert not g["json_ok"]
             continue
         for k, ev in e.items():
             assert g[k] == ev, f"{label}: rec {i} field {k}: gpu={g[k]!r} ref={ev!r}"

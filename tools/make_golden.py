@@ -80,10 +80,43 @@ def main():
                                tool_calls=[[dict(id="call_vxw1", name="get-pizza-info", args="{}")],
                                            [dict(id="call_vxw2", name="get-pizza-info", args="{}")], []],
                                done_frames=1)))      # :910 exactly one [DONE]
+    # tests/middlewares/mcp_test.go:537 a channel element WITHOUT the "data: " prefix: the agent drops it (agent.go:186-188),
+    # the channel closes, nothing is forwarded and only the final [DONE] is written (agent.go:140-143)
+    bare = raw_strings("tests/middlewares/mcp_test.go", 537, 537)
+    fx.append(dict(name="prefixless_channel_element", source="tests/middlewares/mcp_test.go:537", kind="channel_elements",
+                   iterations=[bare], expect=dict(frames=0, terminated=False, acc_content="", done_frames=1)))
+    audit = audit_coverage(fx)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    json.dump(dict(reference="inference-gateway v0.24.0 @ ebf5d0e", generated_by="tools/make_golden.py", fixtures=fx),
+    json.dump(dict(reference="inference-gateway v0.24.0 @ ebf5d0e", generated_by="tools/make_golden.py", fixtures=fx, audit=audit),
               open(OUT, "w"), indent=1, ensure_ascii=False)
     print("wrote", OUT, len(fx), "fixtures", [len(i) for f in fx for i in f["iterations"]])
+    print("audit:", audit["n_literals"], "SSE literals in", audit["files"], "- uncovered:", audit["uncovered"])
+
+
+def audit_coverage(fx):
+    """Every Go string literal under the reference's *_test.go files that holds SSE bytes (starts with "data: " or
+    is a JSON chunk handed to a stream channel) must appear in some fixture above: the list of all of them, with
+    file:line, and the ones no fixture contains (must stay empty)."""
+    have = "\n".join(el for f in fx for it in f["iterations"] for el in it)
+    lits, files = [], set()
+    for root, _, names in os.walk(REF):
+        for nm in names:
+            if not nm.endswith("_test.go"):
+                continue
+            path = os.path.join(root, nm)
+            text = open(path, encoding="utf-8").read()
+            rel = os.path.relpath(path, REF)
+            for m in re.finditer(r"`([^`]*)`", text):
+                lit = m.group(1)
+                if "data: " not in lit and not (lit.startswith("{") and '"choices"' in lit and '"delta"' in lit):
+                    continue
+                line = text.count("\n", 0, m.start()) + 1
+                files.add(rel)
+                for piece in [p for p in lit.split("\n") if p.strip()]:
+                    lits.append(dict(at=f"{rel}:{line}", covered=piece.strip() in have or ("data: " + piece.strip()) in have,
+                                     head=piece.strip()[:60]))
+    return dict(n_literals=len(lits), files=sorted(files), uncovered=[l for l in lits if not l["covered"]],
+                where=sorted(set(l["at"] for l in lits)))
 
 
 if __name__ == "__main__":
