@@ -198,6 +198,45 @@ def time_steps(torch, fn, steps):
     return ev0.elapsed_time(ev1)
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pins this rank to the CPU cores of the NUMA node its GPU hangs off (sysfs local_cpulist of the GPU's PCI function), so
+    that the pinned staging buffers the library allocates next are first-touched on that node and the H2D / D2H copies do not
+    cross the socket interconnect. Returns a description for the JSON line; None when the topology cannot be read."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        cpus = open(os.path.join(path, "local_cpulist")).read().strip()
+        node = int(open(os.path.join(path, "numa_node")).read().strip())
+        want = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            want.update(range(int(lo), int(hi or lo) + 1))
+        want &= os.sched_getaffinity(0)
+        if not want:
+            return None
+        os.sched_setaffinity(0, want)
+        return {"numa_node": node, "cpus": cpus, "bound_threads": len(want)}
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
+def delivered(res):
+    """(frames, frame bytes) a batch result delivers: the inline run of every segment plus the runs linked from it."""
+    cs = np.concatenate([[0], np.cumsum(res.frames["len"].astype(np.int64))])
+    ff, fc = res.segs["frame_first"].astype(np.int64), res.segs["frame_count"].astype(np.int64)
+    frames, nbytes = int(fc.sum()), int((cs[ff + fc] - cs[ff]).sum())
+    cur = res.segs["next"].astype(np.int64)
+    cur = cur[cur != 0xFFFFFFFF]
+    while cur.size:
+        a, b = res.runs["frame_first"][cur].astype(np.int64), res.runs["frame_count"][cur].astype(np.int64)
+        frames += int(b.sum()); nbytes += int((cs[a + b] - cs[a]).sum())
+        cur = res.runs["next"][cur].astype(np.int64)
+        cur = cur[cur != 0xFFFFFFFF]
+    return frames, nbytes
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -213,6 +252,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.streams is None:
@@ -229,6 +269,8 @@ def main():
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = None if args.no_numa else bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries exactly one JSON line: NCCL printf()s its version banner to stdout when the communicator is created
@@ -286,17 +328,9 @@ def main():
     counts = dict(frames=int(res.raw.n_frames), recs=int(res.raw.n_recs), tcs=int(res.raw.n_tcs), usages=int(res.raw.n_usages),
                   out_bytes=int(res.raw.out_bytes), text_bytes=int(res.raw.text_bytes), runs=int(res.raw.n_runs),
                   in_bytes=in_payload, segs=n_segs, events=n_events)
-    valid_frames = int(res.segs["frame_count"].astype(np.int64).sum()) + sum(
-        int(res.runs["frame_count"][j]) for j in range(int(res.raw.n_runs)))
-    counts["frames"] = valid_frames        # frames of lines after a terminating chunk are allocated but cut from the result
-    # bytes of the delivered frames (b_out of SURVEY 8(d)), wherever they live: materialised in the out arena or spans of the input
-    cs = np.concatenate([[0], np.cumsum(res.frames["len"].astype(np.int64))])
-    ff, fc = res.segs["frame_first"].astype(np.int64), res.segs["frame_count"].astype(np.int64)
-    frame_bytes = int((cs[ff + fc] - cs[ff]).sum())
-    for j in range(int(res.raw.n_runs)):
-        a, b = int(res.runs["frame_first"][j]), int(res.runs["frame_count"][j])
-        frame_bytes += int(cs[a + b] - cs[a])
-    counts["frame_bytes"] = frame_bytes
+    # frames of lines after a terminating chunk are allocated but cut from the result (their runs are unlinked): count what
+    # is delivered, and its bytes (b_out of SURVEY 8(d)) wherever they live -- the out arena or spans of the input
+    counts["frames"], counts["frame_bytes"] = delivered(res)
     counts["zero_copy_frames"] = int(np.count_nonzero(res.frames["off"] >= res.in_base))
     terminated = int(np.count_nonzero(res.segs["flags"] & 1))
     ok_recs = int(np.count_nonzero(res.recs["flags"] & 1))
@@ -341,12 +375,11 @@ def main():
         torch.cuda.synchronize()
         seg_frames = 0
         for sl, ns in piece_meta:      # frames of the last warm-up step (sanity: the same chunks come out)
-            r = eng.download(sl, stream)
-            seg_frames += int(r.segs["frame_count"].astype(np.int64).sum()) + sum(int(r.runs["frame_count"][j]) for j in range(int(r.raw.n_runs)))
+            seg_frames += delivered(eng.download(sl, stream))[0]
         sync_all()
         seg_ms = sh.max_over_ranks(time_steps(torch, seg_step, args.steps), world)
         seg_tot = sh.reduce_counters({"f": seg_frames}, world)["f"]
-        segmented = {"pieces_per_stream": k, "launches_per_step": 2 * k, "value": seg_tot * args.steps / (seg_ms / 1e3), "unit": UNIT,
+        segmented = {"pieces_per_stream": k, "launches_per_step": (2 if args.flags & 4 else 6) * k, "value": seg_tot * args.steps / (seg_ms / 1e3), "unit": UNIT,
                      "ms_per_step": seg_ms / args.steps, "chunks_emitted_per_step": seg_tot,
                      "note": "seeded random TCP cuts; every piece is its own micro-batch, unterminated tails are carried on the device"}
         if seg_frames != counts["frames"]:
@@ -372,8 +405,7 @@ def main():
         for i in range(3):
             strong_step(i)
         torch.cuda.synchronize()
-        r = eng.download(s_meta[2][0], stream)
-        s_frames = int(r.segs["frame_count"].astype(np.int64).sum()) + sum(int(r.runs["frame_count"][j]) for j in range(int(r.raw.n_runs)))
+        s_frames = delivered(eng.download(s_meta[2][0], stream))[0]
         sync_all()
         s_ms = sh.max_over_ranks(time_steps(torch, strong_step, args.steps), world)
         s_tot = sh.reduce_counters({"f": s_frames, "n": len(my)}, world)
@@ -480,7 +512,9 @@ def main():
         line["c5_strong"] = strong
     if e2e:
         line["e2e"] = e2e
+    line["config"]["numa"] = numa or "not bound"
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
+        os.sched_setaffinity(0, all_cpus)          # the CPU arm gets every core the process may use, not just the GPU's node
         try:
             line["cpu_baseline"] = cpu_baseline(bodies, mode, host_threads())
         except Exception as ex:  # the checker library is test infrastructure; report, do not hide

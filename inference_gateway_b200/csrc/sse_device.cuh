@@ -9,6 +9,7 @@
 //   out, frames, recs, tcs, usages, text, runs, seg_results   per-batch results (see include/sse_gpu.h)
 //   ctr     Counters                   bump allocators + work ticket, zeroed per launch
 #pragma once
+#include <cstddef>
 #include <stdint.h>
 #include "../../include/sse_gpu.h"
 
@@ -25,17 +26,19 @@ struct ConnState {
 #endif
 #define SSE_LEN_BUCKETS (4096 >> SSE_LEN_SHIFT)
 #define SSE_N_BUCKETS (32 * SSE_LEN_BUCKETS)
-struct Counters {
+struct alignas(8) Counters {
     uint32_t ticket;       // next segment to process
+    uint32_t n_tcs;
+    // two 8-byte pairs: the produce kernel allocates a round's output with ONE 64-bit atomicAdd per pair (low word | high word
+    // << 32) instead of four 32-bit ones; every counter stays below 2^31 (capacities are 31-bit), so the low word never carries
     uint32_t out_bytes;
+    uint32_t n_items;      // split pipeline: work items written by the produce kernel
     uint32_t n_frames;
     uint32_t n_recs;
-    uint32_t n_tcs;
     uint32_t n_usages;
     uint32_t text_bytes;
     uint32_t n_runs;
     int32_t  status;
-    uint32_t n_items;      // split pipeline: work items written by the produce kernel
     uint32_t item_ticket;  // split pipeline: next item batch for the decode kernel
     uint32_t n_tiles;      // fused pipeline: tiles written by the plan kernel
     uint32_t reserved1;
@@ -45,6 +48,10 @@ struct Counters {
     uint32_t class_count[SSE_N_BUCKETS];  // split pipeline: items per bucket (see item_bucket)
     uint32_t class_cursor[SSE_N_BUCKETS];
 };
+
+static_assert(offsetof(Counters, out_bytes) % 8 == 0 && offsetof(Counters, n_items) == offsetof(Counters, out_bytes) + 4 &&
+              offsetof(Counters, n_frames) % 8 == 0 && offsetof(Counters, n_recs) == offsetof(Counters, n_frames) + 4,
+              "the produce kernel adds to (out_bytes, n_items) and (n_frames, n_recs) with one 64-bit atomic each");
 
 struct KParams {
     const uint8_t *in;

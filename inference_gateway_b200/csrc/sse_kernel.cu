@@ -254,11 +254,13 @@ sse_stream_kernel(const __grid_constant__ KParams P) {
                     __syncwarp();
                 }
                 uint32_t ob = 0, fb = 0, rb = 0;
-                if (lane == 0) {
-                    if (SPLIT && tot_q) qb = atomicAdd(&P.ctr->n_items, tot_q);
-                    if (tot_b) ob = atomicAdd(&P.ctr->out_bytes, (tot_b + 15u) & ~15u);
-                    if (tot_f) fb = atomicAdd(&P.ctr->n_frames, tot_f);
-                    if (tot_r) rb = atomicAdd(&P.ctr->n_recs, tot_r);
+                if (lane == 0) {     // the round's allocation: two 64-bit atomics (Counters: out_bytes | n_items, n_frames | n_recs)
+                    const unsigned long long a0 = (unsigned long long)((tot_b + 15u) & ~15u) | ((unsigned long long)tot_q << 32);
+                    const unsigned long long a1 = (unsigned long long)tot_f | ((unsigned long long)tot_r << 32);
+                    unsigned long long r0 = 0, r1 = 0;
+                    if (a0) r0 = atomicAdd(reinterpret_cast<unsigned long long *>(&P.ctr->out_bytes), a0);
+                    if (a1) r1 = atomicAdd(reinterpret_cast<unsigned long long *>(&P.ctr->n_frames), a1);
+                    ob = (uint32_t)r0; qb = (uint32_t)(r0 >> 32); fb = (uint32_t)r1; rb = (uint32_t)(r1 >> 32);
                 }
                 ob = __shfl_sync(FULL, ob, 0); fb = __shfl_sync(FULL, fb, 0); rb = __shfl_sync(FULL, rb, 0); qb = __shfl_sync(FULL, qb, 0);
                 if (ob + tot_b + 16 > P.cap_out || fb + tot_f > P.cap_frames || rb + tot_r > P.cap_recs ||

@@ -83,6 +83,17 @@ struct Lane {
 #ifndef SSE_LDWIN
 #define SSE_LDWIN 1
 #endif
+template <bool RO> __device__ __forceinline__ uint4 ldwin16(const uint8_t *base, uint32_t off);
+// A lane walks its line front to back through 16-byte windows: each window load depends on the previous one having been
+// consumed, so with few resident warps (a steady-state tick) the walk runs at DRAM latency per window. The line is pulled
+// into L1 ahead of the walk instead: PF_AHEAD bytes beyond the window, one prefetch per 128-byte line crossed.
+constexpr uint32_t PF_AHEAD = 384;
+__device__ __forceinline__ void prefetch_l1(const uint8_t *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+template <bool RO>
+__device__ __forceinline__ uint4 ldwin16(const uint8_t *base, uint32_t off, uint32_t end) {
+    if ((off & 127u) == 0 && off + PF_AHEAD < end) prefetch_l1(base + off + PF_AHEAD);
+    return ldwin16<RO>(base, off);
+}
 template <bool RO>
 __device__ __forceinline__ uint4 ldwin16(const uint8_t *base, uint32_t off) {
     const uint4 *p = reinterpret_cast<const uint4 *>(base + (off & ~15u));
@@ -391,7 +402,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
             if (i == 0 && (s0 | s1 | s2 | s3) == 0 && L.p + 16u <= L.pe) {      // a whole window of plain string bytes
                 L.p += 16u; L.slen += 16u;
                 if (L.p >= L.pe) break;
-                L.win = ldwin16<RO>(P.out, L.p);
+                L.win = ldwin16<RO>(P.out, L.p, L.pe);
                 continue;
             }
             unsigned long long lo = ((unsigned long long)s1 << 32) | s0;
@@ -402,7 +413,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
             if (n == 0) break;
             L.p += n; L.slen += n;
             if ((L.p & 15u) != 0 || L.p >= L.pe) break;     // stopped at a special byte or at the end of the payload
-            L.win = ldwin16<RO>(P.out, L.p);
+            L.win = ldwin16<RO>(P.out, L.p, L.pe);
         }
     }
     // phase B: plain automaton steps
@@ -423,7 +434,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
                 L.slen = in_tok ? L.slen + 1 : 0;
                 L.st = t;
                 L.p++;
-                if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldwin16<RO>(P.out, L.p);
+                if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldwin16<RO>(P.out, L.p, L.pe);
             } else pend = t | (cls << 8) | (in_str ? 0x10000u : 0u) | (in_tok ? 0x20000u : 0u);
         }
     }
@@ -441,7 +452,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
         L.sf = in_str ? (L.sf | nf) : (L.sf & ~SF_STRMASK);
         L.slen = (pend & 0x20000u) ? L.slen + 1 : 0;
         L.p++;
-        if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldwin16<RO>(P.out, L.p);
+        if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldwin16<RO>(P.out, L.p, L.pe);
     }
 }
 
@@ -761,6 +772,14 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
     S.recp = nullptr;
     const uint32_t lane = lane_id();
     const uint32_t n_items = min(P.ctr->n_items, P.cap_items);
+    // Items per warp and pull. A full batch (32) is right when there is more work than warps. A steady-state tick (one short
+    // segment per connection) has fewer items than lanes in the grid: the kernel is then bound by the serial latency of a lane
+    // walking its line with 2-3 warps per scheduler, so the items are spread over all warps (8 or 16 lanes each) instead.
+    uint32_t batch = 32;
+    {
+        const uint32_t warps = gridDim.x * (uint32_t)V3_WARPS;
+        if (n_items < 32u * warps) { const uint32_t per = (n_items + warps - 1u) / warps; batch = per <= 8u ? 8u : (per <= 16u ? 16u : 32u); }
+    }
 
     Lane L; L.busy = false; L.p = L.pe = 0; L.win = make_uint4(0, 0, 0, 0);
     L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.km = TRIE_ROOT; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
@@ -769,11 +788,11 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
 
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&P.ctr->item_ticket, 32u);
+        if (lane == 0) base = atomicAdd(&P.ctr->item_ticket, batch);
         base = __shfl_sync(FULL, base, 0);
         if (base >= n_items) break;
         const uint32_t idx = base + lane;
-        const bool has = idx < n_items;
+        const bool has = lane < batch && idx < n_items;
         if (has) {
             const uint4 it = P.items_sorted[idx];
             L.p = it.x; L.plen = it.y & 0x00FFFFFFu; L.pe = it.x + L.plen; L.rec = it.z; L.slot = it.w;   // slot: segment index
@@ -830,7 +849,10 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
                 }
             }
         }
-        if (L.busy && L.p < L.pe) L.win = ldwin16<true>(P.out, L.p);      // the automaton reads the payload through a 16-byte window
+        if (L.busy && L.p < L.pe) {                                       // the automaton reads the payload through a 16-byte window
+            for (uint32_t o = (L.p & ~127u) + 128u; o < L.pe && o < L.p + PF_AHEAD; o += 128u) prefetch_l1(P.out + o);
+            L.win = ldwin16<true>(P.out, L.p);
+        }
         for (;;) {
             const bool any_busy = __any_sync(FULL, L.busy);
             if (any_busy) {

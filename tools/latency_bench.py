@@ -24,13 +24,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--streams", type=int, default=65536)
     ap.add_argument("--rounds", type=int, default=6, help="how many times the stream population is replayed")
+    ap.add_argument("--flags", type=int, default=0, help="sse_config.flags (4 tile kernel, 16 skeleton templates)")
     args = ap.parse_args()
     from inference_gateway_b200 import SseEngine, synth
     streams, mode = synth.make_config("C4", n_streams=args.streams)
     events = [[e + b"\n\n" for e in b.split(b"\n\n") if e] for b, _, _ in streams]
     n_ticks = max(len(e) for e in events)
     tick_bytes = [sum(len(ev[t]) for ev in events if t < len(ev)) for t in range(n_ticks)]
-    eng = SseEngine(device=0, max_conns=args.streams, bytes_per_batch=max(tick_bytes) + 64, n_slots=2, carry_slot_bytes=16384)
+    eng = SseEngine(device=0, max_conns=args.streams, bytes_per_batch=max(tick_bytes) + 64, n_slots=2, carry_slot_bytes=16384, flags=args.flags)
     lat, frames_total, bytes_total = [], 0, 0
     t_start = None
     for r in range(args.rounds + 1):                  # round 0 is warm-up

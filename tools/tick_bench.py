@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--streams", type=int, default=65536)
     ap.add_argument("--tick", type=int, default=2)
     ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--flags", type=int, default=0, help="sse_config.flags (4 tile kernel, 16 skeleton templates)")
     args = ap.parse_args()
     import torch
     from inference_gateway_b200 import SseEngine, synth
@@ -25,7 +26,7 @@ def main():
     evs = [[e + b"\n\n" for e in b.split(b"\n\n") if e] for b, _, _ in streams]
     items = [(c, mode, ev[args.tick]) for c, ev in enumerate(evs) if args.tick < len(ev)]
     nbytes = sum(len(d) for _, _, d in items)
-    eng = SseEngine(device=0, max_conns=args.streams, bytes_per_batch=nbytes + 16 * len(items) + 64, n_slots=1)
+    eng = SseEngine(device=0, max_conns=args.streams, bytes_per_batch=nbytes + 16 * len(items) + 64, n_slots=1, carry_slot_bytes=16384, flags=args.flags)
     stream = torch.cuda.Stream()
     slot, arena, segs = eng.acquire()
     n, nb = eng.fill(arena, segs, items)
