@@ -513,7 +513,7 @@ def main():
     if e2e:
         line["e2e"] = e2e
     line["config"]["numa"] = numa or "not bound"
-    if rank == 0 and not args.no_cpu_baseline and world >= 1:
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
         os.sched_setaffinity(0, all_cpus)          # the CPU arm gets every core the process may use, not just the GPU's node
         try:
             line["cpu_baseline"] = cpu_baseline(bodies, mode, host_threads())

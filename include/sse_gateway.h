@@ -7,7 +7,7 @@
  *   ssegw_pump                      one tick of the per-GPU batcher
  *   ssegw_recv                      `line, ok := <-streamCh` (api/routes.go:602-606, mcp/agent.go:171)
  *   ssegw_agent_recv and friends    mcp.Agent.RunWithStream for one iteration (mcp/agent.go:126-290, final [DONE] :140-143)
- *   ssegw_proxy_stream / _step    handleStreamingRequest, the raw /proxy/:provider/*path stream loop (api/routes.go:129-232)
+ *   ssegw_proxy_stream / _step    handleStreamingRequest, the raw /proxy/:provider/... stream loop (api/routes.go:129-232)
  *   ssegw_mcp_writer_step           one turn of handleMCPStreamingRequest's writer (api/middlewares/mcp.go:253-299): the
  *                                   terminal-frame rule (:261-268) and the upstream-error sniff that may set 503 (:272-280)
  */

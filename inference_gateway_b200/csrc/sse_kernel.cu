@@ -1,4 +1,4 @@
-// sse_kernel.cu -- stage 1 of the default pipeline (produce), and the fused first-generation kernel.
+// sse_kernel.cu -- stage 1 of the default pipeline (produce).
 //
 // One persistent warp per connection segment (dynamic ticket):
 //   stage    carry tail (HBM, per connection) + new segment bytes -> warp-private shared-memory window
@@ -6,10 +6,10 @@
 //   classify strings.TrimSpace / Contains "[DONE]" / HasPrefix "data: "   (agent.go:178-193), or verbatim (mode P)
 //   emit     frame table; a frame that stands in the input arena as it must be sent is a span of it (zero-copy), the others
 //            go through the warp-cooperative serializer into the out arena      (agent.go:195 / routes.go:613)
-//   SPLIT = true  (default pipeline): a stub record + a 16-byte work item per line to decode; sse_kernel2.cu sorts the
-//                 items, decodes them (sse_decode_kernel) and resolves early termination (sse_finalize_kernel)
-//   SPLIT = false (SSE_FLAG_KERNEL_V1): one lane per line runs the sequential decoder decode_chunk right here, then
-//                 early termination (agent.go:235-242); an independent second implementation kept for the tests
+//   items    a stub record + a 16-byte work item per line to decode (lines longer than the window are assembled in the carry
+//            slot and become work items too); sse_kernel2.cu sorts the items, decodes them (sse_decode_kernel) and resolves
+//            early termination (sse_finalize_kernel). The template parameter SPLIT is always true: the first-generation
+//            kernel that decoded in place (SPLIT = false) was removed in round 2.
 //   finish   carry update, per-segment result
 //
 // Pure integer/byte work, no tensor cores.
@@ -20,7 +20,7 @@
 namespace {
 
 // ---------------------------------------------------------------- the kernel
-// SPLIT = false: the complete v1 kernel. SPLIT = true: stage 1 of the split pipeline (no JSON decoder in this instantiation).
+// stage 1 of the pipeline (no JSON decoder in this kernel)
 #ifndef SSE_V1_MINB
 #define SSE_V1_MINB 2
 #endif

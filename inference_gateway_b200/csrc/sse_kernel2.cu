@@ -1,4 +1,4 @@
-// sse_kernel2.cu -- stages 2-4 of the default pipeline (work-item sort, decode, finalize), and the fused v2 kernel.
+// sse_kernel2.cu -- stages 2-4 of the default pipeline: work-item sort, decode, finalize.
 //
 // The table-driven automaton (v2_round / v2_action / v2_finish_line): one lane per line steps a pushdown automaton over the
 // payload it reads through a 16-byte register window. Syntax, type compatibility and field capture follow json.Unmarshal into
@@ -9,8 +9,8 @@
 //   sse_bucket_{hist,scan,scatter}_kernel  counting sort of the produce stage's work items by (length, shape class)
 //   sse_decode_kernel                      persistent, one CTA per SM: warps pull 32 sorted items and run the automaton
 //   sse_finalize_kernel                    early termination (agent.go:235-242): cut a segment's runs after its terminating chunk
-//   sse_stream_kernel_v2 (SSE_FLAG_KERNEL_V2)  the earlier fused design: every warp an autonomous producer/consumer
-//       (stage + split + classify + serialize, ring of work items, the same automaton as consumer); kept for the tests
+//   sse_decode_kernel<TPL=true>            the same with skeleton-template replay in front of the automaton (SSE_FLAG_TEMPLATES;
+//                                          opt-in: measured slower)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "sse_common.cuh"
@@ -83,17 +83,6 @@ struct Lane {
 #ifndef SSE_LDWIN
 #define SSE_LDWIN 1
 #endif
-template <bool RO> __device__ __forceinline__ uint4 ldwin16(const uint8_t *base, uint32_t off);
-// A lane walks its line front to back through 16-byte windows: each window load depends on the previous one having been
-// consumed, so with few resident warps (a steady-state tick) the walk runs at DRAM latency per window. The line is pulled
-// into L1 ahead of the walk instead: PF_AHEAD bytes beyond the window, one prefetch per 128-byte line crossed.
-constexpr uint32_t PF_AHEAD = 384;
-__device__ __forceinline__ void prefetch_l1(const uint8_t *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
-template <bool RO>
-__device__ __forceinline__ uint4 ldwin16(const uint8_t *base, uint32_t off, uint32_t end) {
-    if ((off & 127u) == 0 && off + PF_AHEAD < end) prefetch_l1(base + off + PF_AHEAD);
-    return ldwin16<RO>(base, off);
-}
 template <bool RO>
 __device__ __forceinline__ uint4 ldwin16(const uint8_t *base, uint32_t off) {
     const uint4 *p = reinterpret_cast<const uint4 *>(base + (off & ~15u));
@@ -402,7 +391,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
             if (i == 0 && (s0 | s1 | s2 | s3) == 0 && L.p + 16u <= L.pe) {      // a whole window of plain string bytes
                 L.p += 16u; L.slen += 16u;
                 if (L.p >= L.pe) break;
-                L.win = ldwin16<RO>(P.out, L.p, L.pe);
+                L.win = ldwin16<RO>(P.out, L.p);
                 continue;
             }
             unsigned long long lo = ((unsigned long long)s1 << 32) | s0;
@@ -413,7 +402,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
             if (n == 0) break;
             L.p += n; L.slen += n;
             if ((L.p & 15u) != 0 || L.p >= L.pe) break;     // stopped at a special byte or at the end of the payload
-            L.win = ldwin16<RO>(P.out, L.p, L.pe);
+            L.win = ldwin16<RO>(P.out, L.p);
         }
     }
     // phase B: plain automaton steps
@@ -434,7 +423,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
                 L.slen = in_tok ? L.slen + 1 : 0;
                 L.st = t;
                 L.p++;
-                if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldwin16<RO>(P.out, L.p, L.pe);
+                if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldwin16<RO>(P.out, L.p);
             } else pend = t | (cls << 8) | (in_str ? 0x10000u : 0u) | (in_tok ? 0x20000u : 0u);
         }
     }
@@ -452,7 +441,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
         L.sf = in_str ? (L.sf | nf) : (L.sf & ~SF_STRMASK);
         L.slen = (pend & 0x20000u) ? L.slen + 1 : 0;
         L.p++;
-        if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldwin16<RO>(P.out, L.p, L.pe);
+        if ((L.p & 15u) == 0 && L.p < L.pe) L.win = ldwin16<RO>(P.out, L.p);
     }
 }
 
@@ -849,10 +838,7 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
                 }
             }
         }
-        if (L.busy && L.p < L.pe) {                                       // the automaton reads the payload through a 16-byte window
-            for (uint32_t o = (L.p & ~127u) + 128u; o < L.pe && o < L.p + PF_AHEAD; o += 128u) prefetch_l1(P.out + o);
-            L.win = ldwin16<true>(P.out, L.p);
-        }
+        if (L.busy && L.p < L.pe) L.win = ldwin16<true>(P.out, L.p);      // the automaton reads the payload through a 16-byte window
         for (;;) {
             const bool any_busy = __any_sync(FULL, L.busy);
             if (any_busy) {

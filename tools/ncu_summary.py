@@ -27,7 +27,7 @@ HEAD = {"produce": "stage 1 of the split pipeline: sse_stream_kernel<SPLIT=true>
                    "zero-copy frames are not serialized)",
         "decode": "stage 3 of the split pipeline: sse_decode_kernel (table-driven automaton, one lane per line, items sorted by "
                   "(length, shape))"}
-CMD = "python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+CMD = "python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-strong --segments 0"
 
 
 def raw(rep):
@@ -61,7 +61,7 @@ if os.path.exists(lc):
         name = r[4].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
         per.setdefault(name, []).append(float(r[-1]))
     tot = sum(sum(v) / len(v) for v in per.values())
-    txt = [f"ncu --metrics gpu__time_duration.sum --clock-control none; {CMD}; last two steps, per launch (ns, serialised, cold):"]
+    txt = [f"ncu --metrics gpu__time_duration.sum --clock-control none; {CMD}; two steps of the run, per launch (ns, serialised, cold):"]
     for n, v in per.items():
         a = sum(v) / len(v)
         txt.append(f"  {n:<45s} {a:>12.0f} ns   {100 * a / tot:5.1f} % of the step")
