@@ -167,6 +167,26 @@ def test_mixed_modes_and_folds(engine):
             assert tcalls == ecalls, i
 
 
+def test_bare_done_line_does_not_stop_tool_call_parsing(engine):
+    """agent.go:181-184 swallows every line that contains "[DONE]", but parseStreamingToolCalls only breaks on the exact line
+    "data: [DONE]" (agent.go:394-396): after a bare "[DONE]" (no prefix, or padded) later tool-call chunks still count; after
+    "data: [DONE]" they do not."""
+    tc1 = b'data: {"choices":[{"delta":{"tool_calls":[{"index":0,"id":"a","function":{"name":"first","arguments":"{"}}]}}]}\n\n'
+    tc2 = b'data: {"choices":[{"delta":{"tool_calls":[{"index":0,"function":{"arguments":"}"}},{"index":1,"id":"b","function":{"name":"second"}}]}}]}\n\n'
+    fin = b'data: {"choices":[{"delta":{},"finish_reason":"tool_calls"}]}\n\n'
+    bodies = [tc1 + b"[DONE]\n\n" + tc2 + fin, tc1 + b"  [DONE]  \n\n" + tc2 + fin, tc1 + b"data: [DONE]\n\n" + tc2 + fin,
+              tc1 + b"data: [DONE] \n\n" + tc2 + fin, b"[DONE]\n" + tc1 + tc2 + fin]
+    for nb in (1, 4):
+        outs, views = _run_and_check(engine, bodies, [R] * len(bodies), n_batches=nb, seed=nb, folds=True)
+        names = []
+        for o, v in zip(outs, views):
+            content, has, term, fin_code, calls = agent_results(engine.L, o.agent)
+            assert calls == orc.parse_tool_calls(v.builder) and term and fin_code == 2
+            names.append([c["name"] for c in calls])
+        # "data: [DONE] " trims to the exact line too (strings.TrimSpace first, agent.go:178)
+        assert names == [[b"first", b"second"], [b"first", b"second"], [b"first"], [b"first"], [b"first", b"second"]]
+
+
 # ------------------------------------------------------------------ ragged / edge inputs
 def test_edges(engine):
     nl = b"\n"
