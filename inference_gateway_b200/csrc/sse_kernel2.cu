@@ -454,36 +454,91 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
 #endif
 constexpr int V3_WARPS = SSE_V3_WARPS;
 
-// ---------------------------------------------------------------- skeleton templates, matched by a warp per line
+// ---------------------------------------------------------------- skeleton templates
 // Consecutive chunks of a stream -- and the chunks of every other stream of the same provider -- differ only inside string
-// VALUES and in their numbers: keys, punctuation and literals are byte for byte the same. A line the automaton has walked
-// leaves a template in the CTA's cache (handed from launch to launch through KParams.tcache):
-//   * its SKELETON: the line without the bodies of its value strings and with every digit run outside a string collapsed
-//     to one '0';
-//   * which strings (by ordinal in the line) are wildcards, how many strings and numbers there are;
-//   * what the parse did with the captured ones (content, finish_reason, tool-call fields, usage numbers) and the static rest
-//     of the record.
-// A later line is matched by the WHOLE WARP (w_match): 32 lanes load 512 bytes with one coalesced 16-byte access each, build
-// the quote / digit masks of their 16 bytes (SWAR), get every byte's string ordinal from one warp prefix sum over the quote
-// counts, drop the wildcard bodies and the digits, and compare what is left with the skeleton at the position a second
-// prefix sum gives them. No lane walks the line, so the time for a line does not depend on how many other lines are in
-// flight (a steady-state tick) and nothing is loaded byte by byte. A line with the same skeleton takes the automaton through
-// exactly the same transitions: its record is the template's with its own spans. Anything that is not plain -- a byte
-// below 0x20 or above 0x7E, a backslash, a number with a sign, fraction, exponent, leading zero or more than 18 digits, more
-// than W_MAXSTR strings -- is left to the automaton (and such a line never becomes a template).
-//   [0] next | bucket << 16   [1] skeleton bytes | flags << 16 | tc_count << 24   [2] static record flags
-//   [3] n_choices | n_str << 16 | n_num << 24   [4][5] wildcard strings (bit = ordinal)   [6] n_cap | bytes outside strings << 16
-//   [7][8] capture sources (ordinal | 0x80 for a number)   [9][10] capture ops   [11..14] per-element tool-call flags
-//   [15..] the skeleton
-constexpr uint32_t TF_HAS_USAGE = 1, W_HDR = 15, W_CAP = 5, W_MAXSTR = 48, W_MAXNUM = 16, W_SKEL_MAX = 1000;
-struct WSpan { uint32_t start, len; };
-struct WWarp { uint16_t sstart[W_MAXSTR], send[W_MAXSTR], nstart[W_MAXNUM], nend[W_MAXNUM]; };   // offsets from the line start
-struct WExtra {                    // shared memory of the TPL kernel only
-    WSpan rows[V3_WARPS * 32][W_CAP];   // the captured spans of the line a lane holds
-    WWarp w[V3_WARPS];
-};
-constexpr uint32_t WM_BAD = 0x80000000u, WM_HIT = 0x40000000u;
+// values and integers: keys, punctuation and literals are byte for byte the same. A line the automaton has walked leaves a
+// template in the CTA's cache (handed from launch to launch through KParams.tcache): its bytes outside those wildcards, in
+// runs, and per wildcard what the parse did with it. A later line whose runs compare equal, and whose wildcards are again a
+// well-formed string body / an integer, takes the automaton through exactly the same transitions: its record is the template's
+// with its own spans, and the automaton does not have to run. The work items are sorted by shape, so the 32 lanes of a warp
+// hold lines of the same template and walk it in step.
+//   [0] next | bucket << 16        [1] skeleton bytes | flags << 16 | tc_count << 24     [2] static record flags
+//   [3] n_choices | n_items << 16  [4] the last (up to 4) skeleton bytes  [5] their mask
+//   n_items items (run length | wildcard kind << 16 | op << 24), 4 words of per-element tool-call flags when tc_count > 0,
+//   then the runs (each starts on a word)
+constexpr uint32_t T_LIT_MAX = 1024, TF_HAS_USAGE = 1, TF_SIMPLE = 2, T_HDR = 6;
 
+__device__ __forceinline__ uint32_t gload4(const uint8_t *base, uint32_t off) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(base + (off & ~3u));
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), (off & 3u) * 8u);
+}
+__device__ __forceinline__ uint32_t nondigit4(uint32_t w4) {      // 0x80 in every byte that is not '0'..'9'
+    return (~((w4 | 0x80808080u) - 0x30303030u) | (w4 + 0x46464646u) | w4) & 0x80808080u;
+}
+// body of a string value from fp (just behind the opening quote): position of the closing quote, or SSE_NONE when the body
+// is not well formed (control byte, bad escape, no closing quote). d2: bit 0 escapes, bit 1 invalid UTF-8.
+// 0x80 in some byte of w iff w holds a '"', a '\\', a byte < 0x20 or a byte >= 0x80 (which byte: special_mask4)
+__device__ __forceinline__ uint32_t special_any4(uint32_t w) {
+    const uint32_t q = w ^ 0x22222222u, b = w ^ 0x5C5C5C5Cu;
+    return (((q - 0x01010101u) & ~q) | ((b - 0x01010101u) & ~b) | ((w - 0x20202020u) & ~w) | w) & 0x80808080u;
+}
+// position of the first special byte of the 16-byte window v at or after byte i (16: none)
+__device__ __forceinline__ uint32_t first_special16(const uint4 &v, uint32_t i) {
+    const uint32_t s0 = special_mask4(v.x), s1 = special_mask4(v.y), s2 = special_mask4(v.z), s3 = special_mask4(v.w);
+    unsigned long long lo = ((unsigned long long)s1 << 32) | s0, hi = ((unsigned long long)s3 << 32) | s2;
+    if (i < 8) lo &= ~0ull << (i * 8); else { lo = 0; hi &= ~0ull << ((i - 8) * 8); }
+    return lo ? (uint32_t)(__ffsll((long long)lo) - 1) >> 3 : (hi ? 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3) : 16u);
+}
+// body of a string value from fp (just behind the opening quote): position of the closing quote, or SSE_NONE when the body
+// is not well formed (control byte, bad escape, no closing quote). Returns d2 (bit 0 escapes, bit 1 invalid UTF-8) in the
+// two top bits of the result's companion word *d2p.
+__device__ __noinline__ uint32_t t_scan_string(const uint8_t *base, uint32_t fp, uint32_t pe, uint32_t *d2p) {
+    uint32_t p = fp, d2 = 0;
+    while (p < pe) {
+        uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + (p & ~15u)));
+        if ((p & 15u) == 0) {
+            // whole windows of plain bytes: two loads in flight, one test per window
+            uint4 v2 = __ldg(reinterpret_cast<const uint4 *>(base + p + 16u));
+            while (!(special_any4(v.x) | special_any4(v.y) | special_any4(v.z) | special_any4(v.w))) {
+                p += 16u;
+                if (p >= pe) { *d2p = d2; return SSE_NONE; }
+                v = v2;
+                v2 = __ldg(reinterpret_cast<const uint4 *>(base + p + 16u));
+            }
+        }
+        const uint32_t jb = first_special16(v, p & 15u);
+        const uint32_t q = (p & ~15u) + jb;
+        if (jb == 16u) { p = q; continue; }
+        if (q >= pe) break;
+        const uint32_t c = __ldg(base + q);
+        if (c == '"') { *d2p = d2; return q; }
+        if (c == '\\') {
+            const uint32_t c2 = __ldg(base + q + 1);
+            if (q + 2u <= pe && (c2 == '"' || c2 == '\\' || c2 == '/' || c2 == 'b' || c2 == 'f' || c2 == 'n' || c2 == 'r' || c2 == 't')) p = q + 2u;
+            else if (c2 == 'u' && q + 6u <= pe && hex4(base + q + 2u) >= 0) p = q + 6u;
+            else break;
+            d2 |= 1u;
+        } else if (c >= 0x80u) {
+            const int k = utf8_valid_len(base + q, (int)(pe - q));
+            if (k == 0) { d2 |= 2u; p = q + 1u; } else p = q + (uint32_t)k;      // invalid: the automaton flags it (A_BAD_*) and goes on byte by byte
+        } else break;                                // control byte
+    }
+    *d2p = d2;
+    return SSE_NONE;
+}
+// integer from fp: [-] 0 | [1-9][0-9]*; returns its end, or SSE_NONE
+__device__ __forceinline__ uint32_t t_scan_int(const uint8_t *base, uint32_t fp, uint32_t pe) {
+    uint32_t i = fp;
+    if (i < pe && __ldg(base + i) == '-') i++;
+    if (i >= pe) return SSE_NONE;
+    const uint32_t d0 = __ldg(base + i);
+    if (d0 == '0') return i + 1u;
+    if (d0 - '1' > 8u) return SSE_NONE;
+    i++;
+    while (i + 4u <= pe && nondigit4(gload4(base, i)) == 0) i += 4u;
+    while (i < pe && (uint32_t)__ldg(base + i) - '0' <= 9u) i++;
+    return i;
+}
 __device__ __noinline__ uint32_t t_finish_code(const uint8_t *base, uint32_t s, uint32_t len, uint32_t d2) {
     if (len == 0) return SSE_FIN_NONE;
     uint8_t tmp[40];
@@ -492,6 +547,7 @@ __device__ __noinline__ uint32_t t_finish_code(const uint8_t *base, uint32_t s, 
     for (uint32_t i = 0; i < len; i++) tmp[i] = __ldg(base + s + i);
     return classify_finish(tmp, (int)len);
 }
+
 __device__ __forceinline__ void t_elem_begin(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J, uint32_t static_flags) {
     if (L.sf & SF_TCOPEN) v2_flush_tc(P, L, S, J);
     L.sf |= SF_TCOPEN; L.tc_count++;
@@ -499,240 +555,165 @@ __device__ __forceinline__ void t_elem_begin(const KParams &P, Lane &L, LaneScra
     S.id_off = S.id_len = S.type_off = S.type_len = S.name_off = S.name_len = S.args_off = S.args_len = 0;
 }
 
-__device__ __forceinline__ uint32_t nondigit4(uint32_t w4) {      // 0x80 in every byte that is not '0'..'9'
-    return (~((w4 | 0x80808080u) - 0x30303030u) | (w4 + 0x46464646u) | w4) & 0x80808080u;
-}
-__device__ __forceinline__ uint32_t expand4(uint32_t m4) { return ((m4 * 0x00204081u) & 0x01010101u) * 0xFFu; }   // bit k -> byte k
-__device__ __forceinline__ uint32_t w_bucket(uint32_t skel_len, uint32_t n_str, uint32_t n_num) {
-    return (skel_len * 7u + n_str * 13u + n_num) & (uint32_t)(T_BUCKETS - 1);
-}
-
-// The whole warp scans the line [ps, pe) and compares it with template T (nullptr: only measure the line). Returns
-// WM_BAD (not a plain line: automaton), or bytes outside strings | strings << 16 | numbers << 24, with WM_HIT when T fits. On a
-// hit WW holds the span of every string and number of the line.
-__device__ __noinline__ uint32_t w_match(const uint8_t *__restrict__ base, uint32_t ps, uint32_t pe, const uint32_t *T, WWarp &WW) {
-    const uint32_t lane = lane_id();
-    const uint32_t wm_lo = T ? T[4] : 0u, wm_hi = T ? T[5] : 0u;
-    const uint8_t *skel = reinterpret_cast<const uint8_t *>(T + W_HDR);
-    const uint32_t skel_len = T ? (T[1] & 0xFFFFu) : 0u;
-    uint32_t cq = 0, ck = 0, cn = 0, co = 0, dprev = 0, diff = 0;
+// Walk the line [ps, pe) along template T. APPLY = false: compare the runs, scan the wildcards, take content / finish_reason
+// (registers only); true: (after a successful compare) run every capture op into the lane state. SYNC: all lanes of the
+// warp are in the call (act: this lane has a line and a candidate) and meet after every item. Returns false when the line
+// does not fit. vflags: 0x80000000 an integer needs a range check (second walk).
+template <bool APPLY, bool SYNC>
+__device__ __forceinline__ bool t_walk(const KParams &P, const uint32_t *T, Lane &L, LaneScratch &S, LaneJobs *J, uint32_t ps, uint32_t pe,
+                                       uint32_t &vflags, bool act) {
+    const uint8_t *base = P.out;
+    const uint32_t n_items = act ? T[3] >> 16 : 0u, tc_count = act ? T[1] >> 24 : 0u;
+    const uint32_t *items = T + T_HDR;
+    const uint8_t *tc_static = reinterpret_cast<const uint8_t *>(items + n_items);
+    const uint32_t *lw = items + n_items + (tc_count ? 4u : 0u);
+    uint32_t fp = ps;
+    int cur_ord = -1;
+    bool ok = act;
+    if (!APPLY && act) { L.content_off = L.content_len = 0; L.finish = SSE_FIN_NONE; L.sf &= ~(SF_CDEC | SF_CBAD); }   // captures of an earlier candidate
     #pragma unroll 1
-    for (uint32_t c = ps & ~15u; c < pe; c += 512u) {
-        const uint32_t pos0 = c + 16u * lane;
-        uint4 v = make_uint4(0x61616161u, 0x61616161u, 0x61616161u, 0x61616161u);
-        uint32_t valid = 0;
-        if (pos0 < pe && pos0 + 16u > ps) {
-            v = __ldg(reinterpret_cast<const uint4 *>(base + pos0));
-            valid = 0xFFFFu;
-            if (pos0 < ps) valid &= 0xFFFFu << (ps - pos0);
-            if (pos0 + 16u > pe) valid &= 0xFFFFu >> (pos0 + 16u - pe);
-            if (valid != 0xFFFFu) {                     // bytes of the neighbours (their newlines) must not count: make them 'a'
-                const uint32_t m0 = expand4(valid & 15u), m1 = expand4((valid >> 4) & 15u), m2 = expand4((valid >> 8) & 15u), m3 = expand4(valid >> 12);
-                v.x = (v.x & m0) | (0x61616161u & ~m0); v.y = (v.y & m1) | (0x61616161u & ~m1);
-                v.z = (v.z & m2) | (0x61616161u & ~m2); v.w = (v.w & m3) | (0x61616161u & ~m3);
+    for (uint32_t i = 0; ; i++) {
+        const bool go = ok && i < n_items;
+        if (SYNC) { if (!__any_sync(FULL, go)) break; } else if (!go) break;
+        if (go) {
+            const uint32_t it = items[i];
+            const uint32_t lit = it & 0xFFFFu, kind = (it >> 16) & 0xFFu, op = it >> 24;
+            if (!APPLY) {
+                uint32_t diff = fp + lit > pe ? 1u : 0u;
+                if (!diff) {
+                    uint32_t j = 0;
+                    #pragma unroll 4
+                    for (; j + 4u <= lit; j += 4u) diff |= gload4(base, fp + j) ^ lw[j >> 2];
+                    if (j < lit) diff |= (gload4(base, fp + j) ^ lw[j >> 2]) & ((1u << ((lit - j) * 8u)) - 1u);
+                }
+                if (diff) ok = false;
             }
-        }
-        // not plain: a control byte, a byte >= 0x80, a backslash (0x7F is let through to the compare: it can only match itself)
-        uint32_t bad = 0;
-        {
-            const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
-            #pragma unroll
-            for (int k = 0; k < 4; k++) { const uint32_t w = w4[k], b = w ^ 0x5C5C5C5Cu; bad |= (((b - 0x01010101u) & ~b) | ((w - 0x20202020u) & ~w) | w) & 0x80808080u; }
-        }
-        if (__any_sync(FULL, bad != 0u)) return WM_BAD;
-        const uint32_t Q = eqmask16(v, 0x22222222u) & valid;
-        const uint32_t D = (gather4(~nondigit4(v.x) & 0x80808080u) | (gather4(~nondigit4(v.y) & 0x80808080u) << 4) |
-                            (gather4(~nondigit4(v.z) & 0x80808080u) << 8) | (gather4(~nondigit4(v.w) & 0x80808080u) << 12)) & valid;
-        // quotes before this lane (all quotes are real: there is no backslash in the line)
-        uint32_t qpre = __popc(Q);
-        #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, qpre, d); if ((int)lane >= d) qpre += t; }
-        const uint32_t qtot = __shfl_sync(FULL, qpre, 31);
-        const uint32_t qbefore = cq + qpre - __popc(Q);
-        uint32_t x = Q; x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8;            // bit i: parity of the quotes at or below i
-        const uint32_t ins = (((x << 1) ^ ((qbefore & 1u) ? 0xFFFFu : 0u)) & ~Q) & valid;  // strictly inside a string
-        // the lane's quotes: where strings start and end, and which of its bytes are wildcard bodies
-        uint32_t wild = 0;
-        {
-            uint32_t m = Q, cur = qbefore, posb = 0;
-            for (;;) {
-                const uint32_t nq = m ? (uint32_t)__ffs(m) - 1u : 16u;
-                const uint32_t so = cur >> 1;
-                if ((cur & 1u) && ((so < 32u ? (wm_lo >> so) : (wm_hi >> (so - 32u))) & 1u) && so < 64u) wild |= ((1u << nq) - 1u) & ~((1u << posb) - 1u);
-                if (!m) break;
-                if (so < W_MAXSTR) { if (cur & 1u) WW.send[so] = (uint16_t)(pos0 + nq - ps); else WW.sstart[so] = (uint16_t)(pos0 + nq + 1u - ps); }
-                posb = nq + 1u; cur++; m &= m - 1u;
-            }
-        }
-        // digit runs outside strings: the first digit stays (compared as '0'), the others are dropped
-        const uint32_t Dout = D & ~ins;
-        uint32_t pd = __shfl_up_sync(FULL, Dout >> 15, 1);
-        if (lane == 0) pd = dprev;
-        const uint32_t nd = __shfl_down_sync(FULL, Dout & 1u, 1);
-        const uint32_t Dstart = Dout & ~((Dout << 1) | pd) & 0xFFFFu;
-        const uint32_t Dend = Dout & ~((Dout >> 1) | ((lane == 31 ? 0u : nd) << 15));       // (a run that crosses the chunk ends in the next one)
-        const uint32_t K = valid & ~wild & ~(Dout & ~Dstart);
-        uint32_t pre2 = __popc(K) | ((uint32_t)__popc(valid & ~ins & ~(Dout & ~Dstart)) << 10) | ((uint32_t)__popc(Dstart) << 20);
-        const uint32_t own2 = pre2;
-        #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, pre2, d); if ((int)lane >= d) pre2 += t; }
-        const uint32_t tot2 = __shfl_sync(FULL, pre2, 31);
-        const uint32_t kbefore = ck + ((pre2 - own2) & 0x3FFu), nbefore = cn + ((pre2 - own2) >> 20);
-        {   // number spans
-            if (lane == 0 && dprev && !(Dout & 1u) && cn >= 1u && cn <= W_MAXNUM) WW.nend[cn - 1u] = (uint16_t)(pos0 - ps);   // a run ended exactly at the chunk boundary
-            uint32_t m = Dstart;
-            while (m) { const uint32_t i = (uint32_t)__ffs(m) - 1u; m &= m - 1u; const uint32_t o = nbefore + (uint32_t)__popc(Dstart & ((1u << i) - 1u)); if (o < W_MAXNUM) WW.nstart[o] = (uint16_t)(pos0 + i - ps); }
-            m = Dend;
-            if (lane == 31 && (Dout >> 15) && c + 512u < pe) m &= 0x7FFFu;                    // continues in the next chunk
-            while (m) { const uint32_t i = (uint32_t)__ffs(m) - 1u; m &= m - 1u; const uint32_t o = nbefore + (uint32_t)__popc(Dstart & ((2u << i) - 1u)) - 1u; if (o < W_MAXNUM) WW.nend[o] = (uint16_t)(pos0 + i + 1u - ps); }
-        }
-        if (T && K) {   // what is kept against the skeleton
-            const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
-            uint32_t r = kbefore;
-            #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                if (K & (1u << i)) {
-                    uint32_t b = (w4[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-                    if (Dstart & (1u << i)) b = '0';
-                    if (r >= skel_len || b != (uint32_t)skel[r]) diff = 1;
-                    r++;
+            fp += lit; lw += (lit + 3u) >> 2;
+            if (kind == WK_END) { if (!APPLY && fp != pe) ok = false; }
+            else if (ok) {
+                uint32_t end, d2 = 0;
+                if (kind == WK_STR) end = t_scan_string(base, fp, pe, &d2); else end = t_scan_int(base, fp, pe);
+                if (end == SSE_NONE) ok = false;
+                else {
+                    const uint32_t code = op & 15u, ord = op >> 4, len = end - fp;
+                    if (!APPLY) {
+                        if (code == OP_CONTENT) {
+                            L.content_off = fp; L.content_len = len;
+                            L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
+                        } else if (code == OP_FINISH) L.finish = t_finish_code(base, fp, len, d2);
+                        else if ((code == OP_CHK_I64 || code == OP_CHK_F32) && len > 18u) vflags |= 0x80000000u;
+                    } else if (code != OP_NONE) {
+                        if (code >= OP_TC_ID && code <= OP_TC_INDEX)
+                            while (cur_ord < (int)ord) { cur_ord++; t_elem_begin(P, L, S, J, tc_static[cur_ord]); }
+                        int64_t v = 0;
+                        switch (code) {
+                        case OP_CONTENT:
+                            L.content_off = fp; L.content_len = len;
+                            L.sf = (L.sf & ~(SF_CDEC | SF_CBAD)) | ((d2 & 1u) ? SF_CDEC : 0u) | ((d2 & 2u) ? SF_CBAD : 0u);
+                            break;
+                        case OP_FINISH: L.finish = t_finish_code(base, fp, len, d2); break;
+                        case OP_TC_ID: S.id_off = fp; S.id_len = len; S.tc_dec = (S.tc_dec & ~3u) | d2; break;
+                        case OP_TC_TYPE: S.type_off = fp; S.type_len = len; S.tc_dec = (S.tc_dec & ~12u) | (d2 << 2); break;
+                        case OP_TC_NAME: S.name_off = fp; S.name_len = len; S.tc_dec = (S.tc_dec & ~0x30u) | (d2 << 4); break;
+                        case OP_TC_ARGS: S.args_off = fp; S.args_len = len; S.tc_dec = (S.tc_dec & ~0xC0u) | (d2 << 6); break;
+                        case OP_TC_INDEX: if (parse_i64(base, (int)fp, (int)end, v)) S.tc_index = v; else L.sf |= SF_TYPE; break;
+                        case OP_U_PROMPT: if (parse_i64(base, (int)fp, (int)end, v)) S.u_prompt = v; else L.sf |= SF_TYPE; break;
+                        case OP_U_COMPLETION: if (parse_i64(base, (int)fp, (int)end, v)) S.u_completion = v; else L.sf |= SF_TYPE; break;
+                        case OP_U_TOTAL: if (parse_i64(base, (int)fp, (int)end, v)) S.u_total = v; else L.sf |= SF_TYPE; break;
+                        case OP_CHK_I64: if (len > 18u && !parse_i64(base, (int)fp, (int)end, v)) L.sf |= SF_TYPE; break;
+                        case OP_CHK_F32: if (len > 18u && f32_overflows(base, (int)fp, (int)end)) L.sf |= SF_TYPE; break;
+                        default: break;
+                        }
+                    }
+                    fp = end;
                 }
             }
         }
-        cq += qtot; ck += tot2 & 0x3FFu; co += (tot2 >> 10) & 0x3FFu; cn += tot2 >> 20;
-        dprev = __shfl_sync(FULL, Dout >> 15, 31);
-        __syncwarp();
+        if (SYNC) __syncwarp();
     }
-    if (cq & 1u) return WM_BAD;                                       // an unterminated string: syntax error, the automaton reports it
-    const uint32_t n_str = cq >> 1;
-    if (n_str > W_MAXSTR || cn > W_MAXNUM || co > 0xFFFu) return WM_BAD;
-    // numbers: 1..18 digits, no leading zero
-    bool nbad = false;
-    if (lane < cn) {
-        const uint32_t a = WW.nstart[lane], b = WW.nend[lane];
-        nbad = b <= a || b - a > 18u || (b - a > 1u && __ldg(base + ps + a) == '0');
+    if (APPLY && act) {                                // elements without captured fields, and the last element
+        while (cur_ord + 1 < (int)tc_count) { cur_ord++; t_elem_begin(P, L, S, J, tc_static[cur_ord]); }
+        if (L.sf & SF_TCOPEN) v2_flush_tc(P, L, S, J);
     }
-    if (__any_sync(FULL, nbad)) return WM_BAD;
-    uint32_t res = co | (n_str << 16) | (cn << 24);               // the shape key: bytes outside strings, strings, numbers
-    if (T && !__any_sync(FULL, diff != 0u) && ck == skel_len && n_str == ((T[3] >> 16) & 0xFFu) && cn == (T[3] >> 24)) res |= WM_HIT;
-    return res;
+    return ok;
 }
 
-// After a hit, lane `dst`'s row receives the spans the template captures.
-__device__ __forceinline__ void w_capture(const uint32_t *T, const WWarp &WW, WSpan *row, uint32_t ps) {
-    const uint32_t lane = lane_id(), n_cap = T[6] & 0xFFFFu;
-    if (lane < n_cap) {
-        const uint32_t src = (reinterpret_cast<const uint8_t *>(T + 7))[lane];
-        const uint32_t o = src & 0x7Fu;
-        WSpan sp;
-        if (src & 0x80u) { sp.start = ps + WW.nstart[o]; sp.len = (uint32_t)WW.nend[o] - WW.nstart[o]; }
-        else { sp.start = ps + WW.sstart[o]; sp.len = (uint32_t)WW.send[o] - WW.sstart[o]; }
-        row[lane] = sp;
-    }
+__device__ __forceinline__ uint32_t t_bucket(const uint8_t *base, uint32_t ps, uint32_t pe) {
+    if (pe - ps < 2u) return 0u;
+    return ((uint32_t)__ldg(base + pe - 1u) * 31u + (uint32_t)__ldg(base + pe - 2u)) & (uint32_t)(T_BUCKETS - 1);
 }
 
-// One lane, its own line: run the template's capture ops on the spans w_capture left (what the automaton's actions would have
-// done at those values), then the static rest.
-__device__ __forceinline__ void w_apply(const KParams &P, const uint32_t *T, const WSpan *row, Lane &L, LaneScratch &S, LaneJobs *J) {
-    const uint8_t *base = P.out;
-    const uint32_t n_cap = T[6] & 0xFFFFu, tc_count = T[1] >> 24, flags = (T[1] >> 16) & 0xFFu;
-    const uint8_t *capop = reinterpret_cast<const uint8_t *>(T + 9), *tc_static = reinterpret_cast<const uint8_t *>(T + 11);
-    L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE; L.finish = SSE_FIN_NONE; L.content_off = L.content_len = 0;
-    L.sf &= ~(SF_CDEC | SF_CBAD);
-    if (flags & TF_HAS_USAGE) L.sf |= SF_USAGE;
-    int cur_ord = -1;
+// Walk the chains: every lane of the warp tries its next candidate in the same iteration (warp-uniform loop), so lanes that
+// need more attempts do not fall out of step. off: first candidate per lane (0: none). Returns the template that fits.
+__device__ __forceinline__ uint32_t t_find(const KParams &P, TCtx &X, Lane &L, LaneScratch &S, uint32_t off, uint32_t &vflags) {
+    uint32_t found = 0;
+    const uint32_t plen = L.pe - L.p;
+    const uint32_t tail = plen >= 4u ? gload4(P.out, L.pe - 4u) : 0u;
     #pragma unroll 1
-    for (uint32_t k = 0; k < n_cap; k++) {
-        const uint32_t code = capop[k] & 15u, ord = capop[k] >> 4, fp = row[k].start, len = row[k].len, end = fp + len;
-        if (code >= OP_TC_ID && code <= OP_TC_INDEX)
-            while (cur_ord < (int)ord) { cur_ord++; t_elem_begin(P, L, S, J, tc_static[cur_ord]); }
-        int64_t v = 0;
-        switch (code) {
-        case OP_CONTENT: L.content_off = fp; L.content_len = len; break;
-        case OP_FINISH: L.finish = t_finish_code(base, fp, len, 0); break;
-        case OP_TC_ID: S.id_off = fp; S.id_len = len; break;
-        case OP_TC_TYPE: S.type_off = fp; S.type_len = len; break;
-        case OP_TC_NAME: S.name_off = fp; S.name_len = len; break;
-        case OP_TC_ARGS: S.args_off = fp; S.args_len = len; break;
-        case OP_TC_INDEX: if (parse_i64(base, (int)fp, (int)end, v)) S.tc_index = v; else L.sf |= SF_TYPE; break;
-        case OP_U_PROMPT: if (parse_i64(base, (int)fp, (int)end, v)) S.u_prompt = v; else L.sf |= SF_TYPE; break;
-        case OP_U_COMPLETION: if (parse_i64(base, (int)fp, (int)end, v)) S.u_completion = v; else L.sf |= SF_TYPE; break;
-        case OP_U_TOTAL: if (parse_i64(base, (int)fp, (int)end, v)) S.u_total = v; else L.sf |= SF_TYPE; break;
-        default: break;
+    while (__any_sync(FULL, off != 0u)) {
+        // candidates whose last skeleton bytes differ from the line's are passed over right here
+        while (off && (plen < 4u || ((tail ^ X.store[off + 4u]) & X.store[off + 5u]))) off = X.store[off] & 0xFFFFu;
+        uint32_t vf = 0;
+        const bool fit = t_walk<false, true>(P, X.store + off, L, S, nullptr, L.p, L.pe, vf, off != 0u);
+        if (off) {
+            if (fit) { found = off; off = 0; vflags = vf; }
+            else off = X.store[off] & 0xFFFFu;
         }
     }
-    while (cur_ord + 1 < (int)tc_count) { cur_ord++; t_elem_begin(P, L, S, J, tc_static[cur_ord]); }
-    if (L.sf & SF_TCOPEN) v2_flush_tc(P, L, S, J);
-    L.n_choices = T[3] & 0xFFFFu;
-    if (T[2] & SSE_F_TC_NONNIL) L.sf |= SF_TCNONNIL;
+    return found;
 }
 
-// One lane (under TCtx::build_lock): the line [ps, pe) the automaton has just decoded without error, with the values it
-// recorded, becomes a template -- unless it is not plain (see above) or does not fit the limits.
-__device__ __noinline__ void w_build(const KParams &P, TCtx &X, const TRec &R, uint32_t ps, uint32_t pe, uint32_t rec_static, uint32_t tflags,
+// The automaton has just retired a line it recorded: turn the recording into a template (the caller holds the build lock).
+__device__ __noinline__ void t_build(const KParams &P, TCtx &X, const TRec &R, uint32_t ps, uint32_t pe, uint32_t rec_static, uint32_t tflags,
                                      uint32_t n_choices, uint32_t tc_count, uint32_t tc_first) {
     const uint8_t *base = P.out;
-    if (tc_count > 15u || pe - ps < 4u || pe - ps > 0xFFF0u) return;
-    const uint32_t off = X.used;
-    if (off + W_HDR + (W_SKEL_MAX + 3u) / 4u > (uint32_t)TS_WORDS) return;
-    uint32_t *T = X.store + off;
-    uint8_t *skel = reinterpret_cast<uint8_t *>(T + W_HDR);
-    uint8_t *capsrc = reinterpret_cast<uint8_t *>(T + 7), *capop = reinterpret_cast<uint8_t *>(T + 9);
-    T[7] = T[8] = T[9] = T[10] = 0;
-    uint32_t n_skel = 0, n_str = 0, n_num = 0, n_cap = 0, ev = 0, wm_lo = 0, wm_hi = 0, seen = 0, out_len = 0;
-    bool in_str = false, wild = false, prev_digit = false;
-    for (uint32_t p = ps; p < pe; p++) {
-        const uint32_t c = __ldg(base + p);
-        if (c < 0x20u || c >= 0x80u || c == '\\') return;
-        bool keep = true;
-        if (c == '"') {
-            if (!in_str) {
-                if (n_str >= W_MAXSTR) return;
-                while (ev < R.n && R.ev[ev].start < p + 1u) ev++;                      // (events are in document order)
-                wild = ev < R.n && R.ev[ev].kind == WK_STR && R.ev[ev].start == p + 1u;
-                if (wild) {
-                    seen++;
-                    if (n_str < 32u) wm_lo |= 1u << n_str; else wm_hi |= 1u << (n_str - 32u);
-                    const uint32_t code = R.ev[ev].op & 15u;
-                    if (code != OP_NONE) { if (n_cap >= W_CAP) return; capsrc[n_cap] = (uint8_t)n_str; capop[n_cap] = R.ev[ev].op; n_cap++; }
-                }
-            } else { wild = false; n_str++; }
-            in_str = !in_str; prev_digit = false;
-        } else if (in_str) { keep = !wild; }
-        else if (c - '0' <= 9u) {
-            if (prev_digit) keep = false;
-            else {
-                if (n_num >= W_MAXNUM) return;
-                while (ev < R.n && R.ev[ev].start < p) ev++;
-                if (ev < R.n && R.ev[ev].kind == WK_INT && R.ev[ev].start == p) {
-                    seen++;
-                    const uint32_t code = R.ev[ev].op & 15u;
-                    if (code != OP_NONE && code != OP_CHK_I64 && code != OP_CHK_F32) { if (n_cap >= W_CAP) return; capsrc[n_cap] = (uint8_t)(0x80u | n_num); capop[n_cap] = R.ev[ev].op; n_cap++; }
-                } else return;                                                         // a number the automaton did not see as an integer
-                n_num++;
-            }
-            prev_digit = true;
-        } else { if (c == '-' || c == '+' || c == '.') return; prev_digit = false; }
-        if (c == '"' || (!in_str && keep)) out_len++;                         // outside strings (quotes included), digit runs as one byte
-        if (keep) {
-            if (n_skel >= W_SKEL_MAX) return;
-            skel[n_skel++] = (uint8_t)((!in_str && c - '0' <= 9u && c != '"') ? '0' : c);
-        }
+    if (tc_count > 15u || pe - ps < 4u) return;
+    const uint32_t n_items = R.n + 1u;
+    uint32_t prev = ps, litw = 0, litb = 0;
+    for (uint32_t i = 0; i < R.n; i++) {
+        const uint32_t s = R.ev[i].start, e = s + R.ev[i].len;
+        if (s < prev || e > pe || s - prev > 0xFFFFu) return;
+        litw += (s - prev + 3u) >> 2; litb += s - prev; prev = e;
     }
-    if (in_str || seen != R.n) return;              // every value the automaton recorded must have been placed
-    const uint32_t skel_len = n_skel;
-    while (n_skel & 3u) skel[n_skel++] = 0;                                            // (padding is outside skel_len)
-    const uint32_t words = W_HDR + ((skel_len + 3u) >> 2);
-    if (out_len > 0xFFFu) return;
-    const uint32_t bucket = w_bucket(out_len, n_str, n_num);
-    T[1] = skel_len | (tflags << 16) | (tc_count << 24); T[2] = rec_static; T[3] = n_choices | (n_str << 16) | (n_num << 24);
-    T[4] = wm_lo; T[5] = wm_hi; T[6] = n_cap | (out_len << 16);
+    if (pe - prev > 0xFFFFu) return;
+    litw += (pe - prev + 3u) >> 2; litb += pe - prev;
+    if (litb > T_LIT_MAX) return;
+    const uint32_t words = T_HDR + n_items + (tc_count ? 4u : 0u) + litw;
+    const uint32_t off = X.used;
+    if (off + words > (uint32_t)TS_WORDS) return;
+    uint32_t *T = X.store + off;
     {
+        const uint32_t endlit = pe - prev, tn = min(endlit, 4u);
+        const uint32_t tmask = tn == 4u ? 0xFFFFFFFFu : tn == 0u ? 0u : ~((1u << ((4u - tn) * 8u)) - 1u);     // the high tn bytes of the last word
+        T[4] = gload4(base, pe - 4u) & tmask; T[5] = tmask;
+        bool simple = !(tflags & TF_HAS_USAGE) && tc_count == 0;
+        for (uint32_t i = 0; i < R.n; i++) { const uint32_t c = R.ev[i].op & 15u; if (c != OP_NONE && c != OP_CONTENT && c != OP_FINISH && c != OP_CHK_I64 && c != OP_CHK_F32) simple = false; }
+        if (simple) tflags |= TF_SIMPLE;
+    }
+    const uint32_t endlit = pe - prev;
+    const uint32_t bucket = endlit >= 2u ? t_bucket(base, ps, pe) : (uint32_t)T_BUCKETS;      // ends in a wildcard: the catch-all chain
+    T[1] = litb | (tflags << 16) | (tc_count << 24); T[2] = rec_static; T[3] = n_choices | (n_items << 16);
+    uint32_t *items = T + T_HDR, *tcs = items + n_items, *lw = tcs + (tc_count ? 4u : 0u);
+    if (tc_count) {
         uint32_t w4[4] = { 0, 0, 0, 0 }, t = tc_first;
         for (uint32_t j = 0; j < tc_count && t != SSE_NONE; j++) { w4[j >> 2] |= (P.tcs[t].flags & 7u) << ((j & 3u) * 8u); t = P.tcs[t].next; }
-        T[11] = w4[0]; T[12] = w4[1]; T[13] = w4[2]; T[14] = w4[3];
+        tcs[0] = w4[0]; tcs[1] = w4[1]; tcs[2] = w4[2]; tcs[3] = w4[3];
     }
-    for (uint32_t o = X.head[bucket]; o; o = X.store[o] & 0xFFFFu) {                     // stored by another lane meanwhile?
+    prev = ps;
+    for (uint32_t i = 0; i < n_items; i++) {
+        const bool last = i + 1u == n_items;
+        const uint32_t s = last ? pe : R.ev[i].start;
+        const uint32_t lit = s - prev;
+        items[i] = lit | ((last ? (uint32_t)WK_END : (uint32_t)R.ev[i].kind) << 16) | ((last ? 0u : (uint32_t)R.ev[i].op) << 24);
+        for (uint32_t j = 0; j < lit; j += 4u) {
+            uint32_t v = gload4(base, prev + j);
+            if (lit - j < 4u) v &= (1u << ((lit - j) * 8u)) - 1u;
+            *lw++ = v;
+        }
+        prev = last ? pe : s + R.ev[i].len;
+    }
+    // the same skeleton may be there already (stored by another lane meanwhile): identical words
+    for (uint32_t o = X.head[bucket]; o; o = X.store[o] & 0xFFFFu) {
         const uint32_t *U = X.store + o;
         bool same = true;
         for (uint32_t i = 1; i < words && same; i++) same = U[i] == T[i];
@@ -750,7 +731,7 @@ struct CtaSmem3 {
     LaneScratch ls[V3_WARPS * 32];
     LaneJobs jobs[V3_WARPS * 32];
 };
-static_assert(sizeof(CtaSmem3) % 16 == 0 && sizeof(CtaSmem3) + sizeof(WExtra) <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(CtaSmem3) <= 227 * 1024, "shared memory budget");
 
 template <bool TPL>
 __global__ void __launch_bounds__(V3_WARPS * 32, 1)
@@ -789,7 +770,6 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
         if (n_items < 32u * warps) { const uint32_t per = (n_items + warps - 1u) / warps; batch = per <= 8u ? 8u : (per <= 16u ? 16u : 32u); }
     }
 
-    uint32_t last_t = 0;               // the template the warp's previous line fitted (the items are sorted by shape)
     Lane L; L.busy = false; L.p = L.pe = 0; L.win = make_uint4(0, 0, 0, 0);
     L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.km = TRIE_ROOT; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
     L.finish = 0; L.ct = L.ct1 = L.sstk = 0; L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
@@ -814,59 +794,47 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
             S.recp = nullptr;
             L.busy = true;
         }
-        // ---- a cached skeleton? the warp takes the batch's lines one after the other (w_match); the lanes whose line fits a
-        //      template then finish their own record (w_apply), the others run the automaton below
+        // ---- a cached skeleton? the chain of the line's bucket first, then the catch-all chain
         if (templates) {
-            WExtra &wx = *reinterpret_cast<WExtra *>(smem_raw + sizeof(CtaSmem3));
-            WWarp &WW = wx.w[threadIdx.x >> 5];
-            const bool cand = has && S.plen >= 4u && !(L.sf & SF_DONELINE);
-            uint32_t toff = 0;
-            const unsigned cm = __ballot_sync(FULL, cand);
+            const bool cand = has && S.plen >= 4u;
+            uint32_t vflags = 0, toff = 0;
+            uint32_t first = cand ? X.head[t_bucket(P.out, L.p, L.pe)] : 0u;
             #pragma unroll 1
-            for (unsigned m = cm; m; m &= m - 1u) {
-                const int i = __ffs(m) - 1;
-                const uint32_t ps = __shfl_sync(FULL, L.p, i), pe = __shfl_sync(FULL, L.pe, i);
-                uint32_t hit = 0;
-                uint32_t r = w_match(P.out, ps, pe, last_t ? X.store + last_t : nullptr, WW);
-#ifdef SSE_WSTAT
-                if (lane == 0) { atomicAdd(&P.tcache[100], 1u); if (r & WM_BAD) atomicAdd(&P.tcache[102], 1u); }
-#endif
-                if (r & WM_HIT) hit = last_t;
-                else if (!(r & WM_BAD)) {             // the line is plain: look its shape up
-                    const uint32_t key3 = r & 0xFFFF0000u, ol = r & 0xFFFFu;
-                    uint32_t o = X.head[w_bucket(ol, (r >> 16) & 0xFFu, r >> 24)];
-                    #pragma unroll 1
-                    for (; o && !hit; o = X.store[o] & 0xFFFFu) {
-                        if (o == last_t || (X.store[o + 6u] >> 16) != ol || (X.store[o + 3u] & 0xFFFF0000u) != key3) continue;
-                        r = w_match(P.out, ps, pe, X.store + o, WW);
-#ifdef SSE_WSTAT
-                        if (lane == 0) atomicAdd(&P.tcache[104], 1u);
-#endif
-                        if (r & WM_HIT) hit = o;
-                    }
+            for (int pass = 0; pass < 2; pass++) {
+                const uint32_t f = t_find(P, X, L, S, first, vflags);
+                if (f) toff = f;
+                const bool miss = cand && !toff && pass == 0;
+                first = miss ? X.head[T_BUCKETS] : 0u;
+                if (!__any_sync(FULL, first != 0u)) break;
+            }
+            const uint32_t *Tm = X.store + toff;
+            const bool simple = toff && ((Tm[1] >> 16) & TF_SIMPLE) && !(vflags & 0x80000000u);
+            const bool full = toff && !simple;
+            if (__any_sync(FULL, full)) {              // usage / tool-call / range-check ops: a second walk runs them
+                if (full) {
+                    L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE; L.finish = SSE_FIN_NONE; L.content_off = L.content_len = 0;
+                    L.sf &= ~(SF_CDEC | SF_CBAD);
+                    if ((Tm[1] >> 16) & TF_HAS_USAGE) L.sf |= SF_USAGE;
                 }
-#ifdef SSE_WSTAT
-                if (lane == 0 && hit) atomicAdd(&P.tcache[101], 1u);
-#endif
-                if (hit) {
-                    last_t = hit;
-                    w_capture(X.store + hit, WW, wx.rows[(threadIdx.x & ~31u) + (uint32_t)i], ps);
-                    if ((int)lane == i) toff = hit;
-                }
-                __syncwarp();
+                uint32_t d = 0;
+                t_walk<true, true>(P, Tm, L, S, J, L.p, L.pe, d, full);
             }
             if (toff) {                                  // the record is written, the lane retires
-                w_apply(P, X.store + toff, wx.rows[threadIdx.x], L, S, J);
+                L.n_choices = Tm[3] & 0xFFFFu;
+                if (Tm[2] & SSE_F_TC_NONNIL) L.sf |= SF_TCNONNIL;
                 L.st = S_END; L.depth = 0; L.p = L.pe;
                 if (v2_finish_line<false>(P, L, S, J)) atomicMin(&P.seg_term[S.slot], S.rec);
                 L.p = L.pe = 0;
-            } else if (cand && X.used + W_HDR + (W_SKEL_MAX + 3u) / 4u <= (uint32_t)TS_WORDS) {     // the automaton takes the line: let it record a template
-                uint32_t m = X.rec_busy;
-                while ((~m) & ((1u << NREC) - 1u)) {
-                    const uint32_t b = (uint32_t)__ffs((~m) & ((1u << NREC) - 1u)) - 1u;
-                    const uint32_t old = atomicCAS(&X.rec_busy, m, m | (1u << b));
-                    if (old == m) { S.recp = &X.rec[b]; X.rec[b].n = 0; X.rec[b].nonsimple = 0; break; }
-                    m = old;
+            } else if (cand) {
+                L.content_off = L.content_len = 0; L.finish = SSE_FIN_NONE; L.sf &= ~(SF_CDEC | SF_CBAD);      // (tried templates left captures behind)
+                if (!(L.sf & SF_DONELINE) && X.used + 360u <= (uint32_t)TS_WORDS) {     // the automaton takes the line: let it record a template
+                    uint32_t m = X.rec_busy;
+                    while ((~m) & ((1u << NREC) - 1u)) {
+                        const uint32_t b = (uint32_t)__ffs((~m) & ((1u << NREC) - 1u)) - 1u;
+                        const uint32_t old = atomicCAS(&X.rec_busy, m, m | (1u << b));
+                        if (old == m) { S.recp = &X.rec[b]; X.rec[b].n = 0; X.rec[b].nonsimple = 0; break; }
+                        m = old;
+                    }
                 }
             }
         }
@@ -883,7 +851,7 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
                         if (TPL && S.recp) {            // keep the line's skeleton as a template (one lane builds at a time)
                             TRec *R = S.recp;
                             if (!R->nonsimple && !(L.sf & (SF_SYN | SF_TYPE | SF_DEPTH | SF_DONELINE)) && atomicCAS(&X.build_lock, 0u, 1u) == 0u) {
-                                w_build(P, X, *R, ps, pe, SSE_F_JSON_OK | ((L.sf & SF_TCNONNIL) ? SSE_F_TC_NONNIL : 0u), (L.sf & SF_USAGE) ? TF_HAS_USAGE : 0u,
+                                t_build(P, X, *R, ps, pe, SSE_F_JSON_OK | ((L.sf & SF_TCNONNIL) ? SSE_F_TC_NONNIL : 0u), (L.sf & SF_USAGE) ? TF_HAS_USAGE : 0u,
                                         L.n_choices, L.tc_count, L.tc_first);
                                 __threadfence_block();
                                 atomicExch(&X.build_lock, 0u);
@@ -1056,7 +1024,7 @@ int sse_v2_prepare(int device) {
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(d, &T, sizeof T, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(sse_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(CtaSmem3) + sizeof(WExtra)));
+    e = cudaFuncSetAttribute(sse_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(sse_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
     if (e != cudaSuccess) return (int)e;
@@ -1068,7 +1036,7 @@ int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int
     sse_bucket_hist_kernel<<<sm_count * 2, 512, 0, (cudaStream_t)stream>>>(p);
     sse_bucket_scan_kernel<<<1, SCAN_TPB, 0, (cudaStream_t)stream>>>(p);
     sse_bucket_scatter_kernel<<<sm_count * 2, SCATTER_TPB, 0, (cudaStream_t)stream>>>(p);
-    if (p.tcache) sse_decode_kernel<true><<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3) + sizeof(WExtra), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
+    if (p.tcache) sse_decode_kernel<true><<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
     else sse_decode_kernel<false><<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
