@@ -73,11 +73,14 @@ def cpu_quota():
 
 
 def host_threads() -> int:
-    """Cores this process may run on (the cgroup / affinity of a 1-GPU lease is smaller than os.cpu_count())."""
+    """Threads for the CPU arm: the cores this process may run on, capped by the container's CPU quota (the GPU boxes of this
+    pool show 128 logical cores in the affinity mask and a CFS quota of 16 CPUs)."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = max(1, len(os.sched_getaffinity(0)))
     except (AttributeError, OSError):
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    q = cpu_quota()
+    return n if q is None else max(1, min(n, int(np.ceil(q))))     # more threads than the quota only get throttled
 
 
 def build_workload(n_streams: int, shard: int, workload: str, n_content=None):
