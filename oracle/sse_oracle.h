@@ -11,7 +11,8 @@
  * makes (bufio.ReadBytes, strings.TrimSpace/Contains/HasPrefix/TrimPrefix/Split,
  * fmt.Sprintf, encoding/json.Unmarshal v1).  It is pinned by:
  *   - the reference's own SSE fixtures and the semantic assertions its tests make on them
- *     (tests/golden/ref_fixtures.json, produced by tools/make_golden.py),
+ *     (tests/golden/ref_fixtures.json, produced by tools/make_golden.py, which also audits that every
+ *     string literal holding SSE bytes in the reference's *_test.go files is one of the fixtures),
  *   - SURVEY.md Appendix B hand-derived vectors,
  *   - a cross-check of the JSON validator/decoder against CPython's json module and an
  *     independent Python model of the typed decode (tests/go_model.py, tests/test_oracle_json.py),
