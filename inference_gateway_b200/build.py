@@ -8,9 +8,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libssegpu.so")
+# SSE_LIB: load this prebuilt library instead (A/B runs of build-time knobs on the GPU box, tools/build_variants.sh); never rebuilt
+LIB = os.environ.get("SSE_LIB") or os.path.join(HERE, "libssegpu.so")
 SOURCES = ["sse_fused.cu", "sse_kernel.cu", "sse_kernel2.cu", "sse_host.cu", "sse_fold.cpp", "sse_gateway.cpp"]
-HEADERS = ["sse_device.cuh", "sse_common.cuh", "sse_tables.h", os.path.join("..", "..", "include", "sse_gpu.h"),
+HEADERS = ["sse_device.cuh", "sse_common.cuh", "sse_tables.h", "sse_fast.h", os.path.join("..", "..", "include", "sse_gpu.h"),
            os.path.join("..", "..", "include", "sse_gateway.h")]
 
 
@@ -22,6 +23,8 @@ def nvcc() -> str:
 
 
 def needs_build() -> bool:
+    if os.environ.get("SSE_LIB"):
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)

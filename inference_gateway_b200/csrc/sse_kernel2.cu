@@ -15,10 +15,12 @@
 #include <stdint.h>
 #include "sse_common.cuh"
 #include "sse_tables.h"
+#include "sse_fast.h"
 
 namespace {
 
 using namespace ssetab;
+using ssefast::KeyHash;
 
 #ifndef SSE_ROUNDS
 #define SSE_ROUNDS 2
@@ -376,16 +378,50 @@ __device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJo
     return terminates;
 }
 
-// One round of the per-lane automaton: KSTEPS plain steps, then the pending action (if any) of every lane.
+// ---- whole-token shortcuts: the automaton's side of ssefast::fast_phases (sse_fast.h)
+#ifndef SSE_FAST_TOKENS
+#define SSE_FAST_TOKENS 1
+#endif
+#ifndef SSE_HOLD
+#define SSE_HOLD 1
+#endif
+static_assert(ssefast::STR_FLAGS == SF_STRMASK, "per-string flag bits");
 template <bool RO, bool REC>
-__device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J) {
+struct FastOps {
+    const KParams &P; const DfaTables &T; Lane &L; LaneScratch &S;
+    __device__ __forceinline__ uint4 ldwin(uint32_t off) const { return ldwin16<RO>(P.out, off); }
+    __device__ __forceinline__ uint32_t field(uint32_t name) const {        // A_KEY_END for a plain lower-case key
+        if (L.skip != 0) return TY_SKIP;
+        const uint32_t f = T.field[lane_top(L) * NNAMES + name];
+        return (f & FIELD_VALID) ? (f & 0x1FFFu) : (uint32_t)TY_SKIP;
+    }
+    __device__ __forceinline__ void number_end(uint32_t end) const { v2_number_end<REC>(P, L, S, end); }
+    __device__ __forceinline__ void lit_null() const { v2_null<REC>(L, S); }
+    __device__ __forceinline__ void lit_bool() const {                          // A_LIT_TRUE / A_LIT_FALSE
+        const uint32_t ty = L.cur & 15u;
+        if (ty == TY_TS) L.sf |= SF_GBAD; else if (ty != TY_SKIP) L.sf |= SF_TYPE;
+    }
+    __device__ __forceinline__ void value_done() const { ::value_done(L); }
+};
+
+// One round of the per-lane automaton: the whole-token shortcuts, the string skip, KSTEPS plain steps, then the pending
+// action (if any) of every lane.
+template <bool RO, bool REC>
+__device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, const KeyHash &KH, Lane &L, LaneScratch &S, LaneJobs *J) {
     uint32_t pend = 0;                       // action | cls << 8 | in_str << 16 | in_tok << 17
+    if (SSE_FAST_TOKENS && !REC) {
+        FastOps<RO, REC> ops{P, T, L, S};
+        ssefast::fast_phases(KH, L, ops);
+    }
     // phase A (once per round, only the lanes inside a long string value): jump to the next '"', '\\', control or non-ASCII
     // byte, up to SKIPW windows. Keeping it out of the step loop means a warp whose lanes are not all in the same phase
     // executes this path once per round, not once per step.
-    if (L.p < L.pe && L.st == S_VSTR && L.km == TRIE_DEAD) {
+    // (the key trie is only consulted at the end of a finish_reason value: every other string value skips from its first byte)
+    bool more = false;                       // still inside the plain bytes of a string after SKIPW windows
+    if (L.p < L.pe && L.st == S_VSTR && (L.km == TRIE_DEAD || (SSE_FAST_TOKENS && ((L.cur >> 9) & 15u) != TG_FINISH))) {
+        int w = 0;
         #pragma unroll 1
-        for (int w = 0; w < SKIPW; w++) {
+        for (; w < SKIPW; w++) {
             const uint32_t i = L.p & 15u;
             const uint32_t s0 = special_mask4(L.win.x), s1 = special_mask4(L.win.y), s2 = special_mask4(L.win.z), s3 = special_mask4(L.win.w);
             if (i == 0 && (s0 | s1 | s2 | s3) == 0 && L.p + 16u <= L.pe) {      // a whole window of plain string bytes
@@ -404,7 +440,12 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
             if ((L.p & 15u) != 0 || L.p >= L.pe) break;     // stopped at a special byte or at the end of the payload
             L.win = ldwin16<RO>(P.out, L.p);
         }
+        more = w == SKIPW;
     }
+    // Lanes of a batch walk lines of one shape whose string values differ in length. While some lane is still skipping through a
+    // long value the others wait in front of their next token (an idle round costs them nothing: the warp runs until its longest
+    // lane is done), so that the tokens behind the value are taken by all lanes together instead of once per straggler.
+    if (SSE_HOLD && __any_sync(FULL, more)) return;
     // phase B: plain automaton steps
     #pragma unroll
     for (int k = 0; k < KSTEPS; k++) {
@@ -725,8 +766,10 @@ __device__ __noinline__ void t_build(const KParams &P, TCtx &X, const TRec &R, u
     X.head[bucket] = off;                                  // published: readers see a complete template
 }
 
+struct DecTables { DfaTables T; KeyHash KH; };       // what sse_v2_prepare uploads and every CTA copies to shared memory
+static_assert(sizeof(DecTables) % 4 == 0, "copied as 32-bit words");
 struct CtaSmem3 {
-    DfaTables T;
+    DecTables D;
     TCtx X;
     LaneScratch ls[V3_WARPS * 32];
     LaneJobs jobs[V3_WARPS * 32];
@@ -735,13 +778,13 @@ static_assert(sizeof(CtaSmem3) <= 227 * 1024, "shared memory budget");
 
 template <bool TPL>
 __global__ void __launch_bounds__(V3_WARPS * 32, 1)
-sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict__ gT) {
+sse_decode_kernel(const __grid_constant__ KParams P, const DecTables *__restrict__ gT) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaSmem3 &cs = *reinterpret_cast<CtaSmem3 *>(smem_raw);
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(gT);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&cs.T);
-        for (int i = threadIdx.x; i < (int)(sizeof(DfaTables) / 4); i += blockDim.x) dst[i] = src[i];
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&cs.D);
+        for (int i = threadIdx.x; i < (int)(sizeof(DecTables) / 4); i += blockDim.x) dst[i] = src[i];
     }
     TCtx &X = cs.X;
     const bool templates = TPL && P.tcache != nullptr;
@@ -753,7 +796,8 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
         if (threadIdx.x == 0) { X.used = loaded; X.loaded = loaded; X.rec_busy = 0; X.build_lock = 0; }
     }
     __syncthreads();
-    const DfaTables &T = cs.T;
+    const DfaTables &T = cs.D.T;
+    const KeyHash &KH = cs.D.KH;
     LaneScratch &S = cs.ls[threadIdx.x];
     LaneJobs *J = &cs.jobs[threadIdx.x];
     LaneJobs *Jw = &cs.jobs[threadIdx.x & ~31u];   // this warp's 32 queues
@@ -844,7 +888,7 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
             if (any_busy) {
                 #pragma unroll 1
                 for (int round = 0; round < ROUNDS; round++) {
-                    v2_round<true, TPL>(P, T, L, S, J);
+                    v2_round<true, TPL>(P, T, KH, L, S, J);
                     if (L.busy && L.p >= L.pe) {
                         const uint32_t ps = L.pe - S.plen, pe = L.pe;
                         if (v2_finish_line<TPL>(P, L, S, J)) atomicMin(&P.seg_term[S.slot], S.rec);   // agent.go:235-242, resolved in stage 3
@@ -997,7 +1041,7 @@ __global__ void sse_finalize_kernel(const KParams P) {
     P.conns[P.segs[s].conn] = ns;
 }
 
-DfaTables *g_tables_dev[16] = { nullptr };
+DecTables *g_tables_dev[16] = { nullptr };
 
 } // namespace
 
@@ -1017,9 +1061,14 @@ int sse_v2_prepare(int device) {
         }
     static const char *fin_names[] = { "stop", "tool_calls", "length", "content_filter", "function_call" };
     static const uint8_t fin_vals[] = { SSE_FIN_STOP, SSE_FIN_TOOL_CALLS, SSE_FIN_LENGTH, SSE_FIN_CONTENT_FILTER, SSE_FIN_FUNCTION_CALL };
-    static ssetab::DfaTables T;
-    if (ssetab::build_tables(T, fs, n, fin_names, fin_vals, 5) != 0) return (int)cudaErrorInvalidValue;
-    DfaTables *d = nullptr;
+    static DecTables T;
+    static const char *names[NNAMES];
+    int n_names = 0;
+    if (ssetab::build_tables(T.T, fs, n, fin_names, fin_vals, 5, names, &n_names) != 0) return (int)cudaErrorInvalidValue;
+    uint8_t ids[NNAMES];
+    for (int i = 0; i < NNAMES; i++) ids[i] = (uint8_t)i;
+    if (ssefast::build_keyhash(T.KH, names, ids, n_names) != 0) return (int)cudaErrorInvalidValue;
+    DecTables *d = nullptr;
     e = cudaMalloc((void **)&d, sizeof T);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(d, &T, sizeof T, cudaMemcpyHostToDevice);
