@@ -203,9 +203,15 @@ SSE_HD void lane_advance(LaneT &L, Ops &ops, uint32_t np, const V4 &w2) {   // p
     }
 }
 
-template <class LaneT, class Ops>
+// REP: how many tokens (a key, or an integer / literal value) a lane may take in one call.
+template <int REP, class LaneT, class Ops>
 SSE_HD void fast_phases(const KeyHash &KH, LaneT &L, Ops &ops) {
     using namespace ssetab;
+#if defined(__CUDA_ARCH__)
+    #pragma unroll 1
+#endif
+    for (int rep = 0; rep < REP; rep++) {
+    const uint32_t p_before = L.p;
     // phase K: [,] "name": ["]  -- a member key of the schema in one step (the table walk takes one transition per byte and
     // the A_KEY_END action). Entry: in front of the comma (S_AFTO), in front of the opening quote (S_KEY / S_OBJ0) or just
     // behind it (S_KSTR, nothing of the key consumed). The single-byte moves below are the table's own transitions.
@@ -222,40 +228,41 @@ SSE_HD void fast_phases(const KeyHash &KH, LaneT &L, Ops &ops) {
             L.st = S_KSTR; L.km = TRIE_ROOT; L.sf &= ~STR_FLAGS; L.slen = 0;
             step1(L, ops);
         }
-        if (L.st == S_KSTR && L.slen == 0u && L.p < L.pe) {
-            auto w2 = L.win;
-            next_window(L, ops, w2);
-            uint32_t v[6], n = 0;
-            view24(L.win, w2, L.p, v);
-            const uint32_t name = fast_key(KH, v, view_avail(L.p, L.pe), &n);
+    }
+    // one 24-byte view serves whichever token stands at p: a key (just behind its opening quote) or a value
+    const bool key_pos = L.st == S_KSTR && L.slen == 0u && L.p < L.pe;
+    bool val_pos = false;
+    if (!key_pos && L.st == S_VAL && L.p < L.pe) { const uint32_t c = cur_byte(L); val_pos = c - '0' <= 9u || c == 'n' || c == 't' || c == 'f'; }
+    if (key_pos || val_pos) {
+        auto w2 = L.win;
+        next_window(L, ops, w2);
+        uint32_t v[6], n = 0;
+        view24(L.win, w2, L.p, v);
+        const uint32_t avail = view_avail(L.p, L.pe);
+        if (key_pos) {
+            const uint32_t name = fast_key(KH, v, avail, &n);
             if (name != 0xFFFFFFFFu) {                                       // = the key's bytes, A_KEY_END, tr[S_COLON][':'] = S_VAL
                 L.cur = ops.field(name); L.st = S_VAL; L.km = TRIE_ROOT; L.slen = 0;
                 lane_advance(L, ops, L.p + n + 2u, w2);
                 if (L.p < L.pe && cur_byte(L) == '"') { L.st = S_VSTR; step1(L, ops); }   // tr[S_VAL]['"'] = S_VSTR
             }
-        }
-    }
-    // phase N: an integer in front of ',' '}' ']', or null / true / false, in one step
-    if (L.st == S_VAL && L.p < L.pe) {
-        const uint32_t c = cur_byte(L);
-        if (c - '0' <= 9u || c == 'n' || c == 't' || c == 'f') {
-            auto w2 = L.win;
-            next_window(L, ops, w2);
-            uint32_t v[6], len = 0;
-            view24(L.win, w2, L.p, v);
-            const uint32_t kind = fast_value(v, view_avail(L.p, L.pe), &len);
+        } else {
+            // phase N: an integer in front of ',' '}' ']', or null / true / false, in one step
+            const uint32_t kind = fast_value(v, avail, &n);
             if (kind != FT_NONE) {
                 if (kind == FT_INT || kind == FT_ZERO) {                     // the walk stands on the delimiter: A_NUM_END, then the delimiter again
                     L.st = kind == FT_ZERO ? (uint32_t)S_NZERO : (uint32_t)S_NINT;
-                    L.slen = len - 1u;
-                    ops.number_end(L.p + len);
+                    L.slen = n - 1u;
+                    ops.number_end(L.p + n);
                 } else if (kind == FT_NULL) ops.lit_null();
                 else ops.lit_bool();
                 ops.value_done();
                 L.km = TRIE_ROOT; L.slen = 0;
-                lane_advance(L, ops, L.p + len, w2);
+                lane_advance(L, ops, L.p + n, w2);
             }
         }
+    }
+    if (L.p == p_before) break;            // nothing taken: the table walk goes on from here
     }
 }
 

@@ -17,6 +17,9 @@
 #include "../inference_gateway_b200/csrc/sse_fast.h"
 
 using namespace ssetab;
+#ifndef FAST_REP
+#define FAST_REP 1
+#endif
 
 struct V4 { uint32_t x, y, z, w; };
 struct Ev { uint32_t kind, a, b, c; bool operator==(const Ev &o) const { return kind == o.kind && a == o.a && b == o.b && c == o.c; } };
@@ -99,7 +102,7 @@ static bool plain_string_byte(uint32_t c) { return !(c == '"' || c == '\\' || c 
 
 static void round(HLane &L, bool fast) {
     uint32_t pend = 0;
-    if (fast) { HOps ops{ L }; ssefast::fast_phases(KH, L, ops); }
+    if (fast) { HOps ops{ L }; ssefast::fast_phases<FAST_REP>(KH, L, ops); }
     // phase A: the string skip (up to 4 windows), bytewise here
     if (L.p < L.pe && L.st == S_VSTR && (L.km == TRIE_DEAD || (fast && L.cur != FINISH_NAME))) {
         uint32_t budget = 64;

@@ -61,24 +61,26 @@ def _payloads():
     return [p for p in out if p and b"\n" not in p]
 
 
-@pytest.fixture(scope="module")
-def checker():
+@pytest.fixture(scope="module", params=[1, 2, 3])
+def checker(request):
     tmp = tempfile.mkdtemp(prefix="fasttok_")
     exe = os.path.join(tmp, "fast_tokens_check")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "fast_tokens_check.cpp")])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-DFAST_REP=%d" % request.param, "-o", exe,
+                           os.path.join(ROOT, "tests", "fast_tokens_check.cpp")])
     names = os.path.join(tmp, "names.txt")
     open(names, "w").write("\n".join(_schema_names()) + "\n")
     corpus = os.path.join(tmp, "corpus.txt")
     open(corpus, "wb").write(b"\n".join(_payloads()) + b"\n")
-    return exe, names, corpus
+    return exe, names, corpus, request.param
 
 
 @pytest.mark.parametrize("seed", [1, 2])
 def test_shortcuts_equal_table_walk(checker, seed):
-    exe, names, corpus = checker
+    exe, names, corpus, rep = checker
     r = subprocess.run([exe, names, corpus, "6000", str(seed)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-4000:]
     st = json.loads(r.stdout)
     # the shortcuts must actually fire on the clean workload: nearly every key, and the integers / literals
     assert st["clean_fast_keys"] > 20 * st["clean_table_key_ends"], st
-    assert st["clean_fast_values"] > 0.2 * st["clean_fast_keys"], st
+    if rep > 1:       # (with one token per round the table walk has consumed a value's first byte before the next round looks at it)
+        assert st["clean_fast_values"] > 0.2 * st["clean_fast_keys"], st
