@@ -41,10 +41,9 @@ struct alignas(8) Counters {
     int32_t  status;
     uint32_t item_ticket;  // split pipeline: next item batch for the decode kernel
     uint32_t n_tiles;      // fused pipeline: tiles written by the plan kernel
-    uint32_t n_slow;       // split pipeline: work items the lite decode pass handed to the full pass (queued in KParams.items)
+    uint32_t reserved1;
     uint32_t overflow;     // SSE_OVF_* bits: which arena was too small
-    uint32_t slow_ticket;  // next batch of that queue
-    uint32_t pad;
+    uint32_t pad[2];
     // device-only tail (the host reads the struct up to here)
     uint32_t class_count[SSE_N_BUCKETS];  // split pipeline: items per bucket (see item_bucket)
     uint32_t class_cursor[SSE_N_BUCKETS];
@@ -93,7 +92,6 @@ __device__ __forceinline__ void sse_overflow(Counters *c, uint32_t which) {
 // launch wrappers (sse_kernel.cu)
 int sse_launch_produce_kernel(const KParams &p, void *stream, int sm_count);           // split pipeline, stage 1
 int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int device);  // split pipeline, stages 2+3
-int sse_decode_finalize_launches(const KParams &p);                                    // how many kernels that call starts
 int sse_v2_prepare(int device);                                                        // builds + uploads the automaton tables
 int sse_fused_prepare(int device);                                                     // fused pipeline: tables + kernel attributes
 int sse_launch_fused(const KParams &p, void *stream, int sm_count, int device);        // plan kernel + fused tile kernel

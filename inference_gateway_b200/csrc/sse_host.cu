@@ -132,7 +132,7 @@ int do_launch(sse_ctx *c, Slot &s, uint32_t n_segs, cudaStream_t st) {
         else {   // default: produce -> sort -> decode (templates / automaton) -> finalize
             e = sse_launch_produce_kernel(p, (void *)st, c->sm_count);
             if (e == 0) e = sse_launch_decode_finalize(p, (void *)st, c->sm_count, c->device);
-            c->launches += 1 + (uint64_t)sse_decode_finalize_launches(p);   // produce; bucket hist/scan/scatter, decode (lite + full pass), finalize
+            c->launches += 6;   // produce, bucket hist/scan/scatter, decode, finalize
         }
         if (e != 0) { cu_ok((cudaError_t)e, "stream kernel launch"); return SSE_ERR_CUDA; }
     }

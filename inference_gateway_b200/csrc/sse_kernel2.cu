@@ -15,12 +15,10 @@
 #include <stdint.h>
 #include "sse_common.cuh"
 #include "sse_tables.h"
-#include "sse_fast.h"
 
 namespace {
 
 using namespace ssetab;
-using ssefast::KeyHash;
 
 #ifndef SSE_ROUNDS
 #define SSE_ROUNDS 2
@@ -54,7 +52,6 @@ struct TCtx {                      // per CTA, shared memory
 struct LaneScratch {               // cold per-lane state (usage ints, the tool-call element being assembled)
     int64_t u_prompt, u_completion, u_total, tc_index;
     uint32_t tc_flags, tc_dec;
-    uint32_t tc_first, tc_prev;        // chain of the chunk's tool-call elements in P.tcs
     uint32_t id_off, id_len, type_off, type_len, name_off, name_len, args_off, args_len;
     TRec *recp;                    // the automaton records this line's wildcards here (nullptr: not recording)
     uint32_t rec, frame, slot, plen;   // the work item: record index, frame index, segment, payload length (read at the line's end only)
@@ -70,14 +67,14 @@ __device__ __forceinline__ void rec_nonsimple(LaneScratch &S) { if (REC && S.rec
 // per-string flags (cleared outside strings) and per-line flags
 constexpr uint32_t SF_ESC = 1, SF_HI = 2, SF_UPPER = 4, SF_BAD = 8, SF_STRMASK = 15;
 constexpr uint32_t SF_SYN = 0x100, SF_TYPE = 0x200, SF_DEPTH = 0x400, SF_GBAD = 0x800, SF_USAGE = 0x1000,
-                   SF_TCNONNIL = 0x2000, SF_TCOPEN = 0x4000, SF_TCVALID = 0x8000, SF_CDEC = 0x10000, SF_RMODE = 0x20000, SF_CBAD = 0x40000, SF_CSET = 0x80000, SF_DONELINE = 0x100000, SF_BAIL = 0x200000;
+                   SF_TCNONNIL = 0x2000, SF_TCOPEN = 0x4000, SF_TCVALID = 0x8000, SF_CDEC = 0x10000, SF_RMODE = 0x20000, SF_CBAD = 0x40000, SF_CSET = 0x80000, SF_DONELINE = 0x100000;
 
 struct Lane {
     uint32_t p, pe;                // out-arena offsets of the payload being decoded
     uint4 win;                     // the 16 bytes containing p
     uint32_t st, depth, skip, sd, cur, km, slen, sf, choices_count, n_choices, finish;
     unsigned long long ct, ct1, sstk;   // container-type bit stack (1 = array), 128 levels
-    uint32_t content_off, content_len, tc_count;
+    uint32_t content_off, content_len, tc_count, tc_first, tc_prev;
     bool busy;
 };
 
@@ -86,38 +83,21 @@ struct Lane {
 #ifndef SSE_LDWIN
 #define SSE_LDWIN 1
 #endif
-#ifndef SSE_PF_WIN
-#define SSE_PF_WIN 0      // > 0: every window load of the decode kernel asks L1 for the sector this many bytes ahead
-#endif
 template <bool RO>
 __device__ __forceinline__ uint4 ldwin16(const uint8_t *base, uint32_t off) {
     const uint4 *p = reinterpret_cast<const uint4 *>(base + (off & ~15u));
-    if (RO && SSE_PF_WIN) asm volatile("prefetch.global.L1 [%0];" :: "l"(base + (off & ~15u) + SSE_PF_WIN));   // (a prefetch never faults)
     return (RO && SSE_LDWIN) ? __ldg(p) : __ldcg(p);
 }
 __device__ __forceinline__ bool lane_live(const Lane &L) {
     return L.sd >= 3 && ((L.sstk >> 10) & 31ull) == N_CHOICE && L.choices_count == 1;
 }
 __device__ __forceinline__ uint32_t lane_top(const Lane &L) { return (uint32_t)((L.sstk >> (5 * (L.sd - 1))) & 31ull); }
-template <bool LITE = false>
 __device__ __forceinline__ void value_done(Lane &L) {
     if (L.depth == 0) { L.st = S_END; return; }
     const uint32_t d = L.depth - 1;
-    const unsigned long long bits = (LITE || d < 64) ? L.ct : L.ct1;      // (the lite pass bails at depth 64)
+    const unsigned long long bits = d < 64 ? L.ct : L.ct1;
     L.st = ((bits >> (d & 63u)) & 1ull) ? (uint32_t)S_AFTA : (uint32_t)S_AFTO;
 }
-
-// ---- the lite pass (SSE_LITE). The decode stage runs twice over compact code instead of once over everything: first the
-// LITE = true instantiation of the automaton below, in which every rare path (escaped or folded keys, an escaped finish_reason,
-// logprobs, extra_content, floats, type mismatches, nesting beyond 64, choices: null) is replaced by a BAIL: the lane drops its
-// line without having written anything and queues the work item for the second pass, which is the full automaton
-// (LITE = false) over that queue. Tool calls are the full pass's too. Same source, so a line the lite pass finishes gets the record the full pass
-// would write. Why: the full loop's hot instructions are spread over ~50 KB of code and the decode kernel stalls on
-// instruction fetch once the whole-token shortcuts are added to it (profiles/r2b_*); the lite loop fits the 32 KB L1.5 I-cache.
-#ifndef SSE_LITE
-#define SSE_LITE 1
-#endif
-__device__ __forceinline__ void lane_bail(Lane &L) { L.sf |= SF_BAIL; L.p = L.pe; L.st = S_END; }
 
 // Span of a captured string: without escapes it is the payload's own bytes (no call, nothing through local memory); the
 // rare decoded case goes through capture() (text-arena allocation + queued warp-cooperative unquote).
@@ -127,13 +107,11 @@ __device__ __forceinline__ Span capture_v2(const KParams &P, LaneJobs *J, uint32
     return capture(cx, (int)s, (int)e, dec, patch);
 }
 
-// Out of line and without a reference to the Lane (a Lane whose address escapes to a call would live in local memory): takes and
-// returns the lane's flag word.
-__device__ __noinline__ uint32_t v2_flush_tc(const KParams &P, uint32_t sf, LaneScratch &S, LaneJobs *J) {
-    if ((S.tc_flags & SSE_TC_HAS_ID) || ((S.tc_flags & SSE_TC_HAS_FUNC) && (S.name_len || S.args_len))) sf |= SF_TCVALID;
-    sf &= ~SF_TCOPEN;
+__device__ void v2_flush_tc(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
+    if ((S.tc_flags & SSE_TC_HAS_ID) || ((S.tc_flags & SSE_TC_HAS_FUNC) && (S.name_len || S.args_len))) L.sf |= SF_TCVALID;
+    L.sf &= ~SF_TCOPEN;
     uint32_t idx = atomicAdd(&P.ctr->n_tcs, 1u);
-    if (idx >= P.cap_tcs) { sse_overflow(P.ctr, SSE_OVF_TCS); return sf; }
+    if (idx >= P.cap_tcs) { sse_overflow(P.ctr, SSE_OVF_TCS); return; }
     sse_tc *rec = &P.tcs[idx];
     Span id = capture_v2(P, J, S.id_off, S.id_off + S.id_len, S.tc_dec & 3, &rec->id_len);
     Span ty = capture_v2(P, J, S.type_off, S.type_off + S.type_len, (S.tc_dec >> 2) & 3, &rec->type_len);
@@ -147,21 +125,18 @@ __device__ __noinline__ uint32_t v2_flush_tc(const KParams &P, uint32_t sf, Lane
     o.id_off = id.off; o.id_len = id.len; o.type_off = ty.off; o.type_len = ty.len;
     o.name_off = nm.off; o.name_len = nm.len; o.args_off = ar.off; o.args_len = ar.len;
     *rec = o;            // queued unquote jobs overwrite the *_len fields when the warp drains them
-    if (S.tc_first == SSE_NONE) S.tc_first = idx; else P.tcs[S.tc_prev].next = idx;
-    S.tc_prev = idx;
-    return sf;
+    if (L.tc_first == SSE_NONE) L.tc_first = idx; else P.tcs[L.tc_prev].next = idx;
+    L.tc_prev = idx;
 }
 
-template <bool LITE>
-__device__ __forceinline__ void v2_elem_begin(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
+__device__ void v2_elem_begin(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
     if (L.skip > 0) { L.cur = TY_SKIP; return; }
     uint32_t nd = lane_top(L);
     if (nd == A_CHOICES) { L.choices_count++; L.cur = TY_STRUCT | (N_CHOICE << 4); }
-    else if (LITE) lane_bail(L);                   // (the lite pass never enters another array of the schema)
     else if (nd == A_TOOLCALLS) {
         L.cur = TY_STRUCT | (N_TC << 4);
         if (lane_live(L)) {
-            if (L.sf & SF_TCOPEN) L.sf = v2_flush_tc(P, L.sf, S, J);
+            if (L.sf & SF_TCOPEN) v2_flush_tc(P, L, S, J);
             L.sf |= SF_TCOPEN; L.tc_count++;
             S.tc_index = 0; S.tc_flags = 0; S.tc_dec = 0;
             S.id_off = S.id_len = S.type_off = S.type_len = S.name_off = S.name_len = S.args_off = S.args_len = 0;
@@ -172,26 +147,21 @@ __device__ __forceinline__ void v2_elem_begin(const KParams &P, Lane &L, LaneScr
     else L.cur = TY_INT;
 }
 
-template <bool REC, bool LITE>
-__device__ __forceinline__ void v2_null(Lane &L, LaneScratch &S) {
+template <bool REC>
+__device__ void v2_null(Lane &L, LaneScratch &S) {
     uint32_t ty = L.cur & 15u, tgt = (L.cur >> 9) & 15u;
-    if (ty == TY_TS) { if (LITE) lane_bail(L); else L.sf &= ~SF_GBAD; return; }
-    if (LITE) {                                      // (lite: the resets that matter to it; tool-call state does not exist there)
-        if (tgt == TG_CHOICES) lane_bail(L);
-        else if (tgt == TG_USAGE) { L.sf &= ~SF_USAGE; S.u_prompt = S.u_completion = S.u_total = 0; }
-        return;
-    }
+    if (ty == TY_TS) { L.sf &= ~SF_GBAD; return; }
     // a reset of captured state is not something a template replays
     if (tgt == TG_CHOICES || (tgt == TG_USAGE && (L.sf & SF_USAGE)) || tgt == TG_TOOLCALLS || tgt == TG_TC_ID || tgt == TG_TC_TYPE || tgt == TG_TC_FUNCTION) rec_nonsimple<REC>(S);
     switch (tgt) {
     case TG_CHOICES:
         L.n_choices = 0; L.choices_count = 0; L.finish = SSE_FIN_NONE; L.content_off = L.content_len = 0;
         L.sf &= ~(SF_CDEC | SF_CBAD | SF_CSET | SF_TCNONNIL | SF_TCOPEN | SF_TCVALID);
-        L.tc_count = 0; S.tc_first = S.tc_prev = SSE_NONE;
+        L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
         break;
     case TG_USAGE: L.sf &= ~SF_USAGE; S.u_prompt = S.u_completion = S.u_total = 0; break;
     case TG_TOOLCALLS:
-        if (lane_live(L)) { L.sf &= ~(SF_TCNONNIL | SF_TCOPEN | SF_TCVALID); L.tc_count = 0; S.tc_first = S.tc_prev = SSE_NONE; }
+        if (lane_live(L)) { L.sf &= ~(SF_TCNONNIL | SF_TCOPEN | SF_TCVALID); L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE; }
         break;
     case TG_TC_ID: if ((L.sf & SF_TCOPEN) && lane_live(L)) { S.tc_flags &= ~SSE_TC_HAS_ID; S.id_off = S.id_len = 0; S.tc_dec &= ~3u; } break;
     case TG_TC_TYPE: if ((L.sf & SF_TCOPEN) && lane_live(L)) { S.tc_flags &= ~SSE_TC_HAS_TYPE; S.type_off = S.type_len = 0; S.tc_dec &= ~12u; } break;
@@ -202,23 +172,11 @@ __device__ __forceinline__ void v2_null(Lane &L, LaneScratch &S) {
     }
 }
 
-template <bool REC, bool LITE>
-__device__ __forceinline__ void v2_number_end(const KParams &P, Lane &L, LaneScratch &S, uint32_t end) {
+template <bool REC>
+__device__ void v2_number_end(const KParams &P, Lane &L, LaneScratch &S, uint32_t end) {
     const uint32_t ty = L.cur & 15u, tgt = (L.cur >> 9) & 15u;
     const bool is_int = L.st == S_NZERO || L.st == S_NINT;
     const uint32_t start = end - L.slen - 1;
-    if (LITE) {                                      // integers into int fields and numbers that are skipped; the rest is the full pass's
-        if (ty == TY_SKIP) return;
-        if (ty != TY_INT || !is_int) { lane_bail(L); return; }
-        if (end - start > 18 || tgt != TG_NONE) {
-            int64_t v;
-            if (!parse_i64(P.out, (int)start, (int)end, v)) L.sf |= SF_TYPE;
-            else if (tgt == TG_PROMPT) S.u_prompt = v;
-            else if (tgt == TG_COMPLETION) S.u_completion = v;
-            else if (tgt == TG_TOTAL) S.u_total = v;
-        }
-        return;
-    }
     if (REC && S.recp && is_int) {
         uint32_t op = OP_NONE;
         if (ty == TY_INT) {
@@ -244,14 +202,13 @@ __device__ __forceinline__ void v2_number_end(const KParams &P, Lane &L, LaneScr
 }
 
 // returns true when the current byte has to be looked up again in the new state
-template <bool REC, bool LITE>
-__device__ __forceinline__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J, uint32_t t) {
+template <bool REC>
+__device__ bool v2_action(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J, uint32_t t) {
     switch (t) {
     case A_OPEN_OBJ: case A_OPEN_ARR: {
         const bool arr = t == A_OPEN_ARR;
-        if (LITE && L.depth >= 64) { lane_bail(L); return false; }
         if (L.depth >= 128) { L.sf |= SF_DEPTH | SF_SYN; L.p = L.pe - 1; L.st = S_END; return false; }
-        if (LITE || L.depth < 64) L.ct = (L.ct & ~(1ull << L.depth)) | ((unsigned long long)arr << L.depth);
+        if (L.depth < 64) L.ct = (L.ct & ~(1ull << L.depth)) | ((unsigned long long)arr << L.depth);
         else L.ct1 = (L.ct1 & ~(1ull << (L.depth - 64))) | ((unsigned long long)arr << (L.depth - 64));
         L.depth++;
         const uint32_t ty = L.cur & 15u;
@@ -259,27 +216,22 @@ __device__ __forceinline__ bool v2_action(const KParams &P, const DfaTables &T, 
         else {
             const uint32_t okmask = arr ? ((1u << TY_SLICE) | (1u << TY_PSLICE))
                                         : ((1u << TY_STRUCT) | (1u << TY_PSTRUCT) | (1u << TY_ROOT) | (1u << TY_GOOGLE));
-            if (!((okmask >> ty) & 1u)) { if (LITE) { lane_bail(L); return false; } L.sf |= (ty == TY_TS) ? SF_GBAD : SF_TYPE; L.skip++; }
+            if (!((okmask >> ty) & 1u)) { L.sf |= (ty == TY_TS) ? SF_GBAD : SF_TYPE; L.skip++; }
             else {
                 const uint32_t sub = (L.cur >> 4) & 31u, tgt = (L.cur >> 9) & 15u;
-                // the lite pass walks the root, choices[], a choice, its delta and usage; tool_calls, logprobs and extra_content are the full pass's
-                if (LITE && !(sub == N_ROOT || sub == N_CHOICE || sub == N_DELTA || sub == N_USAGE || sub == A_CHOICES)) { lane_bail(L); return false; }
                 const bool live = lane_live(L);
                 L.sstk = (L.sstk & ~(31ull << (5 * L.sd))) | ((unsigned long long)sub << (5 * L.sd));
                 L.sd++;
-                if (LITE) {
-                    if (tgt == TG_USAGE) L.sf |= SF_USAGE;
-                    else if (tgt == TG_CHOICES) L.choices_count = 0;
-                } else if (tgt != TG_NONE) {
+                if (tgt != TG_NONE) {
                     if (tgt == TG_USAGE) L.sf |= SF_USAGE;
                     else if (tgt == TG_TC_FUNCTION) { if (live && (L.sf & SF_TCOPEN)) S.tc_flags |= SSE_TC_HAS_FUNC; }
                     else if (tgt == TG_CHOICES) { if (L.n_choices || L.choices_count) rec_nonsimple<REC>(S); L.choices_count = 0; }
                     else if (tgt == TG_TOOLCALLS) {
                         if (live && (L.sf & SF_TCNONNIL)) rec_nonsimple<REC>(S);
-                        if (live) { L.sf = (L.sf | SF_TCNONNIL) & ~(SF_TCOPEN | SF_TCVALID); L.tc_count = 0; S.tc_first = S.tc_prev = SSE_NONE; }
+                        if (live) { L.sf = (L.sf | SF_TCNONNIL) & ~(SF_TCOPEN | SF_TCVALID); L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE; }
                     }
                 }
-                if (!LITE && sub == N_GOOGLE) L.sf &= ~SF_GBAD;
+                if (sub == N_GOOGLE) L.sf &= ~SF_GBAD;
             }
         }
         L.st = arr ? S_ARR0 : S_OBJ0;
@@ -292,19 +244,17 @@ __device__ __forceinline__ bool v2_action(const KParams &P, const DfaTables &T, 
             const uint32_t node = lane_top(L);
             L.sd--;
             if (node == A_CHOICES) L.n_choices = L.choices_count;
-            else if (LITE) { }
-            else if (node == A_TOOLCALLS) { if (lane_live(L) && (L.sf & SF_TCOPEN)) L.sf = v2_flush_tc(P, L.sf, S, J); }
+            else if (node == A_TOOLCALLS) { if (lane_live(L) && (L.sf & SF_TCOPEN)) v2_flush_tc(P, L, S, J); }
             else if (node == N_GOOGLE) { if (L.sf & SF_GBAD) L.sf |= SF_TYPE; }
         }
-        value_done<LITE>(L);
+        value_done(L);
         return false;
     }
     case A_KEY_END: {
         uint32_t cur = TY_SKIP;
         if (L.skip == 0) {
             const uint32_t node = lane_top(L);
-            if (LITE && (L.sf & (SF_ESC | SF_HI))) { lane_bail(L); return false; }
-            if (!LITE && (L.sf & (SF_ESC | SF_HI))) {   // escaped / non-ASCII key: unquote and fold like encoding/json does
+            if (L.sf & (SF_ESC | SF_HI)) {   // escaped / non-ASCII key: unquote and fold like encoding/json does
                 uint8_t tmp[72];
                 uint32_t n = json_unquote(P.out, (int)(L.p - L.slen), (int)L.p, tmp, 64);
                 int f = (n <= 64) ? match_field(c_schema, (int)node, tmp, (int)n) : -1;
@@ -340,7 +290,6 @@ __device__ __forceinline__ bool v2_action(const KParams &P, const DfaTables &T, 
                     break;
                 case TG_FINISH:
                     if (len == 0) L.finish = SSE_FIN_NONE;
-                    else if (LITE && d2) { lane_bail(L); return false; }      // an escaped finish_reason: the full pass unquotes it
                     else if (!d2) { uint32_t nm = T.accept[L.km]; uint32_t fv = nm != 0xFFu ? T.finmap[nm] : 0xFFu; L.finish = fv != 0xFFu ? fv : (uint32_t)SSE_FIN_OTHER; }
                     else {
                         uint8_t tmp[40];
@@ -348,9 +297,6 @@ __device__ __forceinline__ bool v2_action(const KParams &P, const DfaTables &T, 
                         L.finish = (n <= 32) ? classify_finish(tmp, (int)n) : (uint32_t)SSE_FIN_OTHER;
                     }
                     break;
-                default: break;
-                }
-                if (!LITE) switch (tgt) {
                 case TG_TC_ID: if (L.sf & SF_TCOPEN) { S.tc_flags |= SSE_TC_HAS_ID; S.id_off = start; S.id_len = len; S.tc_dec = (S.tc_dec & ~3u) | d2; } break;
                 case TG_TC_TYPE: if (L.sf & SF_TCOPEN) { S.tc_flags |= SSE_TC_HAS_TYPE; S.type_off = start; S.type_len = len; S.tc_dec = (S.tc_dec & ~12u) | (d2 << 2); } break;
                 case TG_NAME: if (L.sf & SF_TCOPEN) { S.name_off = start; S.name_len = len; S.tc_dec = (S.tc_dec & ~0x30u) | (d2 << 4); } break;
@@ -358,29 +304,24 @@ __device__ __forceinline__ bool v2_action(const KParams &P, const DfaTables &T, 
                 default: break;
                 }
             }
-        } else if (ty == TY_TS) { if (LITE) { lane_bail(L); return false; } L.sf &= ~SF_GBAD; }
+        } else if (ty == TY_TS) L.sf &= ~SF_GBAD;
         else if (ty != TY_SKIP) L.sf |= SF_TYPE;
         if (REC && S.recp) rec_event<REC>(S, WK_STR, L.p - L.slen, L.slen, op);
-        value_done<LITE>(L);
+        value_done(L);
         return false;
     }
     case A_BAD_STAY: L.sf |= SF_BAD; L.st = S_VSTR; return false;
     case A_BAD_REDO: L.sf |= SF_BAD; L.st = S_VSTR; return true;
-    case A_NUM_END:
-        if (LITE) { lane_bail(L); return false; }       // (a number the shortcut declined: fraction, exponent, sign, > 18 digits, white space behind it)
-        v2_number_end<REC, LITE>(P, L, S, L.p); value_done<LITE>(L); return true;
+    case A_NUM_END: v2_number_end<REC>(P, L, S, L.p); value_done(L); return true;
     case A_LIT_TRUE: case A_LIT_FALSE: {
-        if (LITE) { lane_bail(L); return false; }
         const uint32_t ty = L.cur & 15u;
         if (ty == TY_TS) L.sf |= SF_GBAD; else if (ty != TY_SKIP) L.sf |= SF_TYPE;
-        value_done<LITE>(L);
+        value_done(L);
         return false;
     }
-    case A_LIT_NULL:
-        if (LITE) { lane_bail(L); return false; }
-        v2_null<REC, LITE>(L, S); value_done<LITE>(L); return false;
-    case A_ELEM_REDO: v2_elem_begin<LITE>(P, L, S, J); if (LITE && (L.sf & SF_BAIL)) return false; L.st = S_VAL; return true;
-    case A_COMMA_ARR: v2_elem_begin<LITE>(P, L, S, J); if (LITE && (L.sf & SF_BAIL)) return false; L.st = S_VAL; return false;
+    case A_LIT_NULL: v2_null<REC>(L, S); value_done(L); return false;
+    case A_ELEM_REDO: v2_elem_begin(P, L, S, J); L.st = S_VAL; return true;
+    case A_COMMA_ARR: v2_elem_begin(P, L, S, J); L.st = S_VAL; return false;
     default:   // A_ERR
         L.sf |= SF_SYN; L.p = L.pe - 1; L.st = S_END;
         return false;
@@ -388,12 +329,12 @@ __device__ __forceinline__ bool v2_action(const KParams &P, const DfaTables &T, 
 }
 
 // A line retires: final syntax check, record, termination bookkeeping (agent.go:205-242).
-template <bool REC, bool LITE>
-__device__ __forceinline__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
+template <bool REC>
+__device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J) {
     bool terminates = false;
     if (!(L.sf & SF_SYN)) {
-        if (!LITE && L.depth == 0 && (L.st == S_NZERO || L.st == S_NINT || L.st == S_NFRAC || L.st == S_NEXP)) {   // (lite: the kernel hands a payload that ends inside a number to the full pass)
-            v2_number_end<REC, false>(P, L, S, L.pe);
+        if (L.depth == 0 && (L.st == S_NZERO || L.st == S_NINT || L.st == S_NFRAC || L.st == S_NEXP)) {
+            v2_number_end<REC>(P, L, S, L.pe);
             L.st = S_END;
         }
         if (L.st != S_END) L.sf |= SF_SYN;
@@ -421,7 +362,7 @@ __device__ __forceinline__ bool v2_finish_line(const KParams &P, Lane &L, LaneSc
             r.flags |= L.finish << SSE_F_FINISH_SHIFT;
             if (L.sf & SF_TCNONNIL) r.flags |= SSE_F_TC_NONNIL;
             if (L.sf & SF_TCVALID) r.flags |= SSE_F_TC_VALID;
-            r.tc_first = L.tc_count ? S.tc_first : SSE_NONE;
+            r.tc_first = L.tc_count ? L.tc_first : SSE_NONE;
             r.tc_count = (uint16_t)min(L.tc_count, 0xFFFFu);
             if ((L.sf & SF_RMODE) && (L.finish == SSE_FIN_STOP || L.finish == SSE_FIN_TOOL_CALLS)) {
                 r.flags |= SSE_F_TERMINATES;
@@ -435,61 +376,62 @@ __device__ __forceinline__ bool v2_finish_line(const KParams &P, Lane &L, LaneSc
     return terminates;
 }
 
-// ---- whole-token shortcuts: the automaton's side of ssefast::fast_phases (sse_fast.h)
-#ifndef SSE_FAST_TOKENS
-#define SSE_FAST_TOKENS 1
+// ---- stragglers inside a long string value. A lane skips at most SKIPW windows of a string per round, so a 4 KB value costs it
+// 64 rounds while the lanes with shorter lines have retired and the warp runs almost empty; the length of a nearly empty launch (a
+// steady-state tick) is exactly that walk. When at most SSE_COOP lanes of the warp are still inside the plain bytes of a string
+// after their own skip, the WHOLE warp finishes each of those strings: 32 lanes x 16 bytes = 512 contiguous bytes per step
+// (coalesced, independent loads), the first lane that sees a '"', '\\', control or non-ASCII byte -- or the end of the payload --
+// gives the stop. Same result as the per-lane skip: the position of the next special byte.
+#ifndef SSE_COOP
+#define SSE_COOP 8
 #endif
-#ifndef SSE_HOLD
-#define SSE_HOLD 0
-#endif
-#ifndef SSE_FASTREP
-#define SSE_FASTREP 2      // a key and its integer / literal value in one round
-#endif
-#ifndef SSE_PF_L2
-#define SSE_PF_L2 0
-#endif
-#ifndef SSE_PF_L1
-#define SSE_PF_L1 0
-#endif
-__device__ __forceinline__ void prefetch_l1(const uint8_t *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
-static_assert(ssefast::STR_FLAGS == SF_STRMASK, "per-string flag bits");
-template <bool RO, bool REC, bool LITE>
-struct FastOps {
-    const KParams &P; const DfaTables &T; Lane &L; LaneScratch &S;
-    __device__ __forceinline__ uint4 ldwin(uint32_t off) const { return ldwin16<RO>(P.out, off); }
-    __device__ __forceinline__ uint32_t field(uint32_t name) const {        // A_KEY_END for a plain lower-case key
-        if (L.skip != 0) return TY_SKIP;
-        const uint32_t f = T.field[lane_top(L) * NNAMES + name];
-        return (f & FIELD_VALID) ? (f & 0x1FFFu) : (uint32_t)TY_SKIP;
+__device__ __forceinline__ uint32_t first_special16_from0(const uint4 &v) {     // index of the first special byte of v, 16: none
+    const uint32_t s0 = special_mask4(v.x), s1 = special_mask4(v.y), s2 = special_mask4(v.z), s3 = special_mask4(v.w);
+    const unsigned long long lo = ((unsigned long long)s1 << 32) | s0, hi = ((unsigned long long)s3 << 32) | s2;
+    return lo ? (uint32_t)(__ffsll((long long)lo) - 1) >> 3 : (hi ? 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3) : 16u);
+}
+template <bool RO>
+__device__ __forceinline__ void coop_string_skip(const KParams &P, Lane &L, unsigned mm) {
+    const uint32_t lane = lane_id();
+    #pragma unroll 1
+    while (mm) {
+        const int src = __ffs(mm) - 1;
+        mm &= mm - 1;
+        uint32_t q = __shfl_sync(FULL, L.p, src);                 // 16-byte aligned: the lane's own skip stopped at a window border
+        const uint32_t qe = __shfl_sync(FULL, L.pe, src);
+        uint32_t pos;
+        #pragma unroll 1
+        for (;;) {
+            const uint32_t off = q + lane * 16u;
+            uint32_t stop = 0xFFFFFFFFu;                         // where this lane's 16 bytes end the run (none: they are all plain)
+            if (off >= qe) stop = qe;
+            else {
+                const uint32_t j = first_special16_from0(ldwin16<RO>(P.out, off));
+                if (off + j >= qe) stop = qe; else if (j < 16u) stop = off + j;
+            }
+            const unsigned hm = __ballot_sync(FULL, stop != 0xFFFFFFFFu);
+            if (hm) { pos = __shfl_sync(FULL, stop, __ffs(hm) - 1); break; }
+            q += 512u;
+        }
+        if ((int)lane == src) {
+            L.slen += pos - L.p; L.p = pos;
+            if (L.p < L.pe) L.win = ldwin16<RO>(P.out, L.p);
+        }
     }
-    __device__ __forceinline__ void number_end(uint32_t end) const { v2_number_end<REC, LITE>(P, L, S, end); }
-    __device__ __forceinline__ void lit_null() const { v2_null<REC, LITE>(L, S); }
-    __device__ __forceinline__ void lit_bool() const {                          // A_LIT_TRUE / A_LIT_FALSE
-        const uint32_t ty = L.cur & 15u;
-        if (ty == TY_TS) L.sf |= SF_GBAD; else if (ty != TY_SKIP) L.sf |= SF_TYPE;
-    }
-    __device__ __forceinline__ void value_done() const { if (!(LITE && (L.sf & SF_BAIL))) ::value_done<LITE>(L); }
-};
+}
 
-// One round of the per-lane automaton: the whole-token shortcuts, the string skip, KSTEPS plain steps, then the pending
-// action (if any) of every lane.
-template <bool RO, bool REC, bool LITE>
-__device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, const KeyHash &KH, Lane &L, LaneScratch &S, LaneJobs *J) {
+// One round of the per-lane automaton: KSTEPS plain steps, then the pending action (if any) of every lane.
+template <bool RO, bool REC>
+__device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J) {
     uint32_t pend = 0;                       // action | cls << 8 | in_str << 16 | in_tok << 17
-    if (SSE_FAST_TOKENS && !REC && (LITE || !SSE_LITE)) {       // (with the lite pass in front, the full pass keeps its code small: no shortcuts)
-        FastOps<RO, REC, LITE> ops{P, T, L, S};
-        ssefast::fast_phases<SSE_FASTREP>(KH, L, ops);
-    }
     // phase A (once per round, only the lanes inside a long string value): jump to the next '"', '\\', control or non-ASCII
     // byte, up to SKIPW windows. Keeping it out of the step loop means a warp whose lanes are not all in the same phase
     // executes this path once per round, not once per step.
-    // (the key trie is only consulted at the end of a finish_reason value: every other string value skips from its first byte)
-    bool more = false;                       // still inside the plain bytes of a string after SKIPW windows
-    if (L.p < L.pe && L.st == S_VSTR && (L.km == TRIE_DEAD || (SSE_FAST_TOKENS && ((L.cur >> 9) & 15u) != TG_FINISH))) {
+    bool more = false;                       // still inside the plain bytes of the string after SKIPW windows
+    if (L.p < L.pe && L.st == S_VSTR && L.km == TRIE_DEAD) {
         int w = 0;
         #pragma unroll 1
         for (; w < SKIPW; w++) {
-            if (SSE_PF_L1 && (L.p & 16u) == 0 && L.p + SSE_PF_L1 < L.pe) prefetch_l1(P.out + L.p + SSE_PF_L1);   // one per 32-byte sector, a few windows ahead
             const uint32_t i = L.p & 15u;
             const uint32_t s0 = special_mask4(L.win.x), s1 = special_mask4(L.win.y), s2 = special_mask4(L.win.z), s3 = special_mask4(L.win.w);
             if (i == 0 && (s0 | s1 | s2 | s3) == 0 && L.p + 16u <= L.pe) {      // a whole window of plain string bytes
@@ -510,10 +452,10 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, c
         }
         more = w == SKIPW;
     }
-    // Lanes of a batch walk lines of one shape whose string values differ in length. While some lane is still skipping through a
-    // long value the others wait in front of their next token (an idle round costs them nothing: the warp runs until its longest
-    // lane is done), so that the tokens behind the value are taken by all lanes together instead of once per straggler.
-    if (SSE_HOLD && __any_sync(FULL, more)) return;
+    if (SSE_COOP) {
+        const unsigned mm = __ballot_sync(FULL, more);
+        if (mm && __popc(mm) <= SSE_COOP) coop_string_skip<RO>(P, L, mm);
+    }
     // phase B: plain automaton steps
     #pragma unroll
     for (int k = 0; k < KSTEPS; k++) {
@@ -540,7 +482,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, c
         uint32_t t = pend & 0xFFu;
         const uint32_t cls = (pend >> 8) & 0xFFu;
         for (;;) {
-            if (!v2_action<REC, LITE>(P, T, L, S, J, t)) break;         // the action chose the next state
+            if (!v2_action<REC>(P, T, L, S, J, t)) break;         // the action chose the next state
             t = T.tr[L.st * NCLS + cls];                     // redo: same byte, new state
             if (t < A_FIRST) { L.st = t; break; }
         }
@@ -658,7 +600,7 @@ __device__ __noinline__ uint32_t t_finish_code(const uint8_t *base, uint32_t s, 
 }
 
 __device__ __forceinline__ void t_elem_begin(const KParams &P, Lane &L, LaneScratch &S, LaneJobs *J, uint32_t static_flags) {
-    if (L.sf & SF_TCOPEN) L.sf = v2_flush_tc(P, L.sf, S, J);
+    if (L.sf & SF_TCOPEN) v2_flush_tc(P, L, S, J);
     L.sf |= SF_TCOPEN; L.tc_count++;
     S.tc_index = 0; S.tc_flags = static_flags; S.tc_dec = 0;
     S.id_off = S.id_len = S.type_off = S.type_len = S.name_off = S.name_len = S.args_off = S.args_len = 0;
@@ -742,7 +684,7 @@ __device__ __forceinline__ bool t_walk(const KParams &P, const uint32_t *T, Lane
     }
     if (APPLY && act) {                                // elements without captured fields, and the last element
         while (cur_ord + 1 < (int)tc_count) { cur_ord++; t_elem_begin(P, L, S, J, tc_static[cur_ord]); }
-        if (L.sf & SF_TCOPEN) L.sf = v2_flush_tc(P, L.sf, S, J);
+        if (L.sf & SF_TCOPEN) v2_flush_tc(P, L, S, J);
     }
     return ok;
 }
@@ -834,31 +776,27 @@ __device__ __noinline__ void t_build(const KParams &P, TCtx &X, const TRec &R, u
     X.head[bucket] = off;                                  // published: readers see a complete template
 }
 
-struct DecTables { DfaTables T; KeyHash KH; };       // what sse_v2_prepare uploads and every CTA copies to shared memory
-static_assert(sizeof(DecTables) % 4 == 0, "copied as 32-bit words");
 struct CtaSmem3 {
-    DecTables D;
+    DfaTables T;
     TCtx X;
     LaneScratch ls[V3_WARPS * 32];
     LaneJobs jobs[V3_WARPS * 32];
 };
 static_assert(sizeof(CtaSmem3) <= 227 * 1024, "shared memory budget");
 
-// LITE: the lite pass (see SSE_LITE above); slowq != 0: the work list is the lite pass's bail queue (P.items, reused: the
-// sort has moved the produce stage's items to P.items_sorted) instead of the sorted items.
-template <bool TPL, bool LITE>
+template <bool TPL>
 __global__ void __launch_bounds__(V3_WARPS * 32, 1)
-sse_decode_kernel(const __grid_constant__ KParams P, const DecTables *__restrict__ gT, const uint32_t slowq) {
+sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict__ gT) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaSmem3 &cs = *reinterpret_cast<CtaSmem3 *>(smem_raw);
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(gT);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&cs.D);
-        for (int i = threadIdx.x; i < (int)(sizeof(DecTables) / 4); i += blockDim.x) dst[i] = src[i];
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&cs.T);
+        for (int i = threadIdx.x; i < (int)(sizeof(DfaTables) / 4); i += blockDim.x) dst[i] = src[i];
     }
     TCtx &X = cs.X;
     const bool templates = TPL && P.tcache != nullptr;
-    if (TPL) {   // the templates learnt by earlier launches (a cache: results never depend on what it holds)
+    {   // the templates learnt by earlier launches (a cache: results never depend on what it holds)
         uint32_t loaded = 1;
         if (templates) loaded = min(max(P.tcache[0], 1u), (uint32_t)TS_WORDS);
         for (uint32_t i = threadIdx.x; i <= (uint32_t)T_BUCKETS; i += blockDim.x) X.head[i] = loaded > 1u ? P.tcache[1u + i] : 0u;
@@ -866,17 +804,14 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DecTables *__restrict
         if (threadIdx.x == 0) { X.used = loaded; X.loaded = loaded; X.rec_busy = 0; X.build_lock = 0; }
     }
     __syncthreads();
-    const DfaTables &T = cs.D.T;
-    const KeyHash &KH = cs.D.KH;
+    const DfaTables &T = cs.T;
     LaneScratch &S = cs.ls[threadIdx.x];
     LaneJobs *J = &cs.jobs[threadIdx.x];
     LaneJobs *Jw = &cs.jobs[threadIdx.x & ~31u];   // this warp's 32 queues
     J->n = 0;
     S.recp = nullptr;
     const uint32_t lane = lane_id();
-    const uint4 *__restrict__ work = slowq ? P.items : P.items_sorted;
-    uint32_t *const ticket = slowq ? &P.ctr->slow_ticket : &P.ctr->item_ticket;
-    const uint32_t n_items = min(slowq ? P.ctr->n_slow : P.ctr->n_items, P.cap_items);
+    const uint32_t n_items = min(P.ctr->n_items, P.cap_items);
     // Items per warp and pull. A full batch (32) is right when there is more work than warps. A steady-state tick (one short
     // segment per connection) has fewer items than lanes in the grid: the kernel is then bound by the serial latency of a lane
     // walking its line with 2-3 warps per scheduler, so the items are spread over all warps (8 or 16 lanes each) instead.
@@ -888,29 +823,27 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DecTables *__restrict
 
     Lane L; L.busy = false; L.p = L.pe = 0; L.win = make_uint4(0, 0, 0, 0);
     L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.km = TRIE_ROOT; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
-    L.finish = 0; L.ct = L.ct1 = L.sstk = 0; L.content_off = L.content_len = 0; L.tc_count = 0; S.tc_first = S.tc_prev = SSE_NONE;
+    L.finish = 0; L.ct = L.ct1 = L.sstk = 0; L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
     S.rec = S.frame = S.slot = S.plen = 0;
 
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(ticket, batch);
+        if (lane == 0) base = atomicAdd(&P.ctr->item_ticket, batch);
         base = __shfl_sync(FULL, base, 0);
         if (base >= n_items) break;
         const uint32_t idx = base + lane;
         const bool has = lane < batch && idx < n_items;
-        bool bailed = false;                       // lite pass: this lane's line goes to the full pass
         if (has) {
-            const uint4 it = work[idx];
+            const uint4 it = P.items_sorted[idx];
             L.p = it.x; S.plen = it.y & 0x00FFFFFFu; L.pe = it.x + S.plen; S.rec = it.z; S.slot = it.w;   // slot: segment index
             S.frame = P.recs[it.z].frame;
             L.st = S_VAL; L.depth = L.skip = L.sd = 0; L.cur = TY_ROOT | (N_ROOT << 4); L.km = TRIE_ROOT; L.slen = 0;
             L.sf = ((it.y & 0x80000000u) ? SF_RMODE : 0u) | ((it.y & 0x40000000u) ? SF_DONELINE : 0u);
             L.choices_count = L.n_choices = 0; L.finish = SSE_FIN_NONE; L.ct = L.ct1 = L.sstk = 0;
-            L.content_off = L.content_len = 0; L.tc_count = 0; S.tc_first = S.tc_prev = SSE_NONE;
+            L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
             S.u_prompt = S.u_completion = S.u_total = 0;
             S.recp = nullptr;
             L.busy = true;
-            if (SSE_PF_L2) for (uint32_t o = (L.p & ~127u) + 128u; o < L.pe; o += 128u) prefetch_l2(P.out + o);   // the rest of the line on its way to L2
         }
         // ---- a cached skeleton? the chain of the line's bucket first, then the catch-all chain
         if (templates) {
@@ -930,7 +863,7 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DecTables *__restrict
             const bool full = toff && !simple;
             if (__any_sync(FULL, full)) {              // usage / tool-call / range-check ops: a second walk runs them
                 if (full) {
-                    L.tc_count = 0; S.tc_first = S.tc_prev = SSE_NONE; L.finish = SSE_FIN_NONE; L.content_off = L.content_len = 0;
+                    L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE; L.finish = SSE_FIN_NONE; L.content_off = L.content_len = 0;
                     L.sf &= ~(SF_CDEC | SF_CBAD);
                     if ((Tm[1] >> 16) & TF_HAS_USAGE) L.sf |= SF_USAGE;
                 }
@@ -941,7 +874,7 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DecTables *__restrict
                 L.n_choices = Tm[3] & 0xFFFFu;
                 if (Tm[2] & SSE_F_TC_NONNIL) L.sf |= SF_TCNONNIL;
                 L.st = S_END; L.depth = 0; L.p = L.pe;
-                if (v2_finish_line<false, false>(P, L, S, J)) atomicMin(&P.seg_term[S.slot], S.rec);
+                if (v2_finish_line<false>(P, L, S, J)) atomicMin(&P.seg_term[S.slot], S.rec);
                 L.p = L.pe = 0;
             } else if (cand) {
                 L.content_off = L.content_len = 0; L.finish = SSE_FIN_NONE; L.sf &= ~(SF_CDEC | SF_CBAD);      // (tried templates left captures behind)
@@ -962,18 +895,15 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DecTables *__restrict
             if (any_busy) {
                 #pragma unroll 1
                 for (int round = 0; round < ROUNDS; round++) {
-                    v2_round<true, TPL, LITE>(P, T, KH, L, S, J);
-                    if (LITE && L.busy && L.p >= L.pe && ((L.sf & SF_BAIL) || (L.st - (uint32_t)S_NMINUS) <= (uint32_t)(S_NEXP - S_NMINUS))) {
-                        L.busy = false; bailed = true;      // nothing has been written for this line (L.pe and S keep the work item)
-                    }
+                    v2_round<true, TPL>(P, T, L, S, J);
                     if (L.busy && L.p >= L.pe) {
                         const uint32_t ps = L.pe - S.plen, pe = L.pe;
-                        if (v2_finish_line<TPL, LITE>(P, L, S, J)) atomicMin(&P.seg_term[S.slot], S.rec);   // agent.go:235-242, resolved in stage 3
+                        if (v2_finish_line<TPL>(P, L, S, J)) atomicMin(&P.seg_term[S.slot], S.rec);   // agent.go:235-242, resolved in stage 3
                         if (TPL && S.recp) {            // keep the line's skeleton as a template (one lane builds at a time)
                             TRec *R = S.recp;
                             if (!R->nonsimple && !(L.sf & (SF_SYN | SF_TYPE | SF_DEPTH | SF_DONELINE)) && atomicCAS(&X.build_lock, 0u, 1u) == 0u) {
                                 t_build(P, X, *R, ps, pe, SSE_F_JSON_OK | ((L.sf & SF_TCNONNIL) ? SSE_F_TC_NONNIL : 0u), (L.sf & SF_USAGE) ? TF_HAS_USAGE : 0u,
-                                        L.n_choices, L.tc_count, S.tc_first);
+                                        L.n_choices, L.tc_count, L.tc_first);
                                 __threadfence_block();
                                 atomicExch(&X.build_lock, 0u);
                             }
@@ -992,7 +922,6 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DecTables *__restrict
                 jm &= jm - 1;
                 LaneJobs &LJ = Jw[leader];
                 const uint32_t nj = LJ.n;
-                #pragma unroll 1
                 for (uint32_t k = 0; k < nj; k++) {
                     const UnquoteJob jb = LJ.j[k];
                     warp_unquote(P.out, jb.s, jb.e, P.text + jb.dst, jb.patch);
@@ -1002,21 +931,6 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DecTables *__restrict
             }
             __syncwarp();
             if (!any_busy) break;
-        }
-        if (LITE) {                                   // the batch's bailed lines, side by side in the full pass's queue
-            const unsigned bm = __ballot_sync(FULL, bailed);
-            if (bm) {
-                uint32_t qb = 0;
-                if (lane == 0) qb = atomicAdd(&P.ctr->n_slow, (uint32_t)__popc(bm));
-                qb = __shfl_sync(FULL, qb, 0);
-                if (bailed) {
-                    uint4 it;
-                    it.x = L.pe - S.plen; it.z = S.rec; it.w = S.slot;
-                    it.y = S.plen | ((L.sf & SF_RMODE) ? 0x80000000u : 0u) | ((L.sf & SF_DONELINE) ? 0x40000000u : 0u);
-                    P.items[qb + (uint32_t)__popc(bm & ((1u << lane) - 1u))] = it;
-                    L.p = L.pe = 0;
-                }
-            }
         }
     }
     // one CTA hands what it has learnt to the next launch (all CTAs see the same kinds of lines)
@@ -1134,7 +1048,7 @@ __global__ void sse_finalize_kernel(const KParams P) {
     P.conns[P.segs[s].conn] = ns;
 }
 
-DecTables *g_tables_dev[16] = { nullptr };
+DfaTables *g_tables_dev[16] = { nullptr };
 
 } // namespace
 
@@ -1154,39 +1068,27 @@ int sse_v2_prepare(int device) {
         }
     static const char *fin_names[] = { "stop", "tool_calls", "length", "content_filter", "function_call" };
     static const uint8_t fin_vals[] = { SSE_FIN_STOP, SSE_FIN_TOOL_CALLS, SSE_FIN_LENGTH, SSE_FIN_CONTENT_FILTER, SSE_FIN_FUNCTION_CALL };
-    static DecTables T;
-    static const char *names[NNAMES];
-    int n_names = 0;
-    if (ssetab::build_tables(T.T, fs, n, fin_names, fin_vals, 5, names, &n_names) != 0) return (int)cudaErrorInvalidValue;
-    uint8_t ids[NNAMES];
-    for (int i = 0; i < NNAMES; i++) ids[i] = (uint8_t)i;
-    if (ssefast::build_keyhash(T.KH, names, ids, n_names) != 0) return (int)cudaErrorInvalidValue;
-    DecTables *d = nullptr;
+    static ssetab::DfaTables T;
+    if (ssetab::build_tables(T, fs, n, fin_names, fin_vals, 5) != 0) return (int)cudaErrorInvalidValue;
+    DfaTables *d = nullptr;
     e = cudaMalloc((void **)&d, sizeof T);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(d, &T, sizeof T, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(sse_decode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
+    e = cudaFuncSetAttribute(sse_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(sse_decode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(sse_decode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
+    e = cudaFuncSetAttribute(sse_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem3));
     if (e != cudaSuccess) return (int)e;
     g_tables_dev[device] = d;
     return 0;
 }
 
-int sse_decode_finalize_launches(const KParams &p) { return (!p.tcache && SSE_LITE) ? 6 : 5; }   // kernels sse_launch_decode_finalize starts
-
 int sse_launch_decode_finalize(const KParams &p, void *stream, int sm_count, int device) {
     sse_bucket_hist_kernel<<<sm_count * 2, 512, 0, (cudaStream_t)stream>>>(p);
     sse_bucket_scan_kernel<<<1, SCAN_TPB, 0, (cudaStream_t)stream>>>(p);
     sse_bucket_scatter_kernel<<<sm_count * 2, SCATTER_TPB, 0, (cudaStream_t)stream>>>(p);
-    if (p.tcache) sse_decode_kernel<true, false><<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device], 0u);
-    else if (SSE_LITE) {      // lite pass over the sorted items, then the full automaton over what it bailed from
-        sse_decode_kernel<false, true><<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device], 0u);
-        sse_decode_kernel<false, false><<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device], 1u);
-    } else sse_decode_kernel<false, false><<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device], 0u);
+    if (p.tcache) sse_decode_kernel<true><<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
+    else sse_decode_kernel<false><<<sm_count, V3_WARPS * 32, sizeof(CtaSmem3), (cudaStream_t)stream>>>(p, g_tables_dev[device]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const int tpb = 256;

@@ -61,9 +61,8 @@ struct DfaTables {
 struct FieldSrc { uint8_t node; const char *name; uint8_t ty, sub, tgt; };
 
 // Returns 0 on success. `fields` is the schema (node, name, ty, sub, tgt); `fin` maps finish values.
-// names_out / n_names_out (optional): the distinct names in name-id order (NNAMES slots), for the key hash of sse_fast.h.
 inline int build_tables(DfaTables &T, const FieldSrc *fields, int n_fields, const char *const *fin_names,
-                        const uint8_t *fin_vals, int n_fin, const char **names_out = nullptr, int *n_names_out = nullptr) {
+                        const uint8_t *fin_vals, int n_fin) {
     memset(&T, 0, sizeof T);
     // ---------------- byte classes
     for (int c = 0; c < 256; c++) {
@@ -184,8 +183,6 @@ inline int build_tables(DfaTables &T, const FieldSrc *fields, int n_fields, cons
         if (id < 0 || insert(fin_names[i], id) != 0) return -1;
         T.finmap[id] = fin_vals[i];
     }
-    if (names_out) for (int i = 0; i < n_names; i++) names_out[i] = names[i];
-    if (n_names_out) *n_names_out = n_names;
     return 0;
 }
 
