@@ -378,8 +378,9 @@ __device__ bool v2_finish_line(const KParams &P, Lane &L, LaneScratch &S, LaneJo
 
 // ---- stragglers inside a long string value. A lane skips at most SKIPW windows of a string per round, so a 4 KB value costs it
 // 64 rounds while the lanes with shorter lines have retired and the warp runs almost empty; the length of a nearly empty launch (a
-// steady-state tick) is exactly that walk. When at most SSE_COOP lanes of the warp are still inside the plain bytes of a string
-// after their own skip, the WHOLE warp finishes each of those strings: 32 lanes x 16 bytes = 512 contiguous bytes per step
+// steady-state tick) is exactly that walk. When at most SSE_COOP lanes of the warp (any number of them when the launch has fewer
+// items than the grid has lanes: then latency is all there is) are still inside the plain bytes of a string after their own skip,
+// the WHOLE warp finishes each of those strings: 32 lanes x 16 bytes = 512 contiguous bytes per step
 // (coalesced, independent loads), the first lane that sees a '"', '\\', control or non-ASCII byte -- or the end of the payload --
 // gives the stop. Same result as the per-lane skip: the position of the next special byte.
 #ifndef SSE_COOP
@@ -422,7 +423,7 @@ __device__ __forceinline__ void coop_string_skip(const KParams &P, Lane &L, unsi
 
 // One round of the per-lane automaton: KSTEPS plain steps, then the pending action (if any) of every lane.
 template <bool RO, bool REC>
-__device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J) {
+__device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, Lane &L, LaneScratch &S, LaneJobs *J, const uint32_t coop_max) {
     uint32_t pend = 0;                       // action | cls << 8 | in_str << 16 | in_tok << 17
     // phase A (once per round, only the lanes inside a long string value): jump to the next '"', '\\', control or non-ASCII
     // byte, up to SKIPW windows. Keeping it out of the step loop means a warp whose lanes are not all in the same phase
@@ -454,7 +455,7 @@ __device__ __forceinline__ void v2_round(const KParams &P, const DfaTables &T, L
     }
     if (SSE_COOP) {
         const unsigned mm = __ballot_sync(FULL, more);
-        if (mm && __popc(mm) <= SSE_COOP) coop_string_skip<RO>(P, L, mm);
+        if (mm && (uint32_t)__popc(mm) <= coop_max) coop_string_skip<RO>(P, L, mm);
     }
     // phase B: plain automaton steps
     #pragma unroll
@@ -821,6 +822,8 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
         if (n_items < 32u * warps) { const uint32_t per = (n_items + warps - 1u) / warps; batch = per <= 8u ? 8u : (per <= 16u ? 16u : 32u); }
     }
 
+    const uint32_t coop_max = batch < 32u ? 32u : (uint32_t)SSE_COOP;      // see coop_string_skip
+
     Lane L; L.busy = false; L.p = L.pe = 0; L.win = make_uint4(0, 0, 0, 0);
     L.st = S_END; L.depth = L.skip = L.sd = 0; L.cur = 0; L.km = TRIE_ROOT; L.slen = 0; L.sf = 0; L.choices_count = L.n_choices = 0;
     L.finish = 0; L.ct = L.ct1 = L.sstk = 0; L.content_off = L.content_len = 0; L.tc_count = 0; L.tc_first = L.tc_prev = SSE_NONE;
@@ -895,7 +898,7 @@ sse_decode_kernel(const __grid_constant__ KParams P, const DfaTables *__restrict
             if (any_busy) {
                 #pragma unroll 1
                 for (int round = 0; round < ROUNDS; round++) {
-                    v2_round<true, TPL>(P, T, L, S, J);
+                    v2_round<true, TPL>(P, T, L, S, J, coop_max);
                     if (L.busy && L.p >= L.pe) {
                         const uint32_t ps = L.pe - S.plen, pe = L.pe;
                         if (v2_finish_line<TPL>(P, L, S, J)) atomicMin(&P.seg_term[S.slot], S.rec);   // agent.go:235-242, resolved in stage 3
